@@ -1,0 +1,29 @@
+// Host API of the NVLink / NVSwitch symmetric-memory collectives (see comm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace b200 {
+
+// Segment tables live in device memory (int64).  Row formats:
+//   all-gather     : [src_rank, src_off_bytes, dst_off_bytes, nbytes, chunk_prefix]   (chunk = ag_chunk_bytes())
+//   reduce-scatter : [full_off_bytes, shard_off_elems, nelems, chunk_prefix]          (chunk = rs_chunk_elems())
+void p2p_all_gather(const std::vector<int64_t>& peer_ptrs, int rank, void* out, const int64_t* seg_table_dev,
+                    int nseg, int64_t total_chunks, int max_ctas, cudaStream_t stream);
+void p2p_reduce_scatter(const std::vector<int64_t>& peer_ptrs, int rank, float* out, const int64_t* seg_table_dev,
+                        int nseg, int64_t total_chunks, bool in_is_bf16, float scale, float* sumsq_out, int max_ctas,
+                        cudaStream_t stream);
+void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const int64_t* seg_table_dev, int nseg,
+                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream);
+// flags: uint32 [slot][16] per rank; scratch: float [slot][16][16] per rank (both in symmetric memory)
+void signal_barrier(const std::vector<int64_t>& flag_ptrs, int rank, int world, int slot, uint32_t seq,
+                    cudaStream_t stream);
+void allreduce_scalars(const std::vector<int64_t>& flag_ptrs, const std::vector<int64_t>& scratch_ptrs, int rank,
+                       int world, int slot, uint32_t seq, float* vals, int k, int op, cudaStream_t stream);
+int64_t ag_chunk_bytes();
+int64_t rs_chunk_elems();
+int comm_max_world();
+int comm_max_scalars();
+
+}  // namespace b200

@@ -1,0 +1,673 @@
+// Memory-bound sm_100a kernels of the ViT training step: LayerNorm fwd/bwd, row softmax fwd/bwd,
+// fused cross-entropy (loss + dlogits), patch im2col, bias-gradient column sums, sum of squares
+// (grad-norm partials) and the fused sharded AdamW update.
+//
+// All of them are 128-bit vectorised, keep a row (or a thread's slice of it) in registers so DRAM is
+// touched once per tensor, and accumulate in fp32.
+//
+// Capability parity (reference = ronghanghu/vit_10b_fsdp_example):
+//   LayerNorm       -> timm Block.norm1/norm2 and FSDPViTModel.norm   (run_vit_training.py:134-141,151)
+//   softmax         -> timm Attention                                  (run_vit_training.py:134)
+//   cross entropy   -> torch.nn.CrossEntropyLoss                       (run_vit_training.py:229,262)
+//   AdamW           -> torch.optim.AdamW over sharded params           (run_vit_training.py:237,278)
+//   sum of squares  -> FSDP.clip_grad_norm_                            (run_vit_training.py:270)
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "elementwise.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kLnThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x), f[1] = bf16_hi(v.x);
+    f[2] = bf16_lo(v.y), f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z), f[5] = bf16_hi(v.z);
+    f[6] = bf16_lo(v.w), f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]);
+    v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]);
+    v.w = pack_bf16x2(f[6], f[7]);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum over the whole CTA of up to two values at once. `red` is 2 * 32 floats of shared memory.
+template <int kThreads>
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    __syncthreads();  // protect `red` from the previous use
+    if (l == 0) {
+        red[w] = a;
+        red[32 + w] = b;
+    }
+    __syncthreads();
+    float ra = (l < kThreads / 32) ? red[l] : 0.f;
+    float rb = (l < kThreads / 32) ? red[32 + l] : 0.f;
+    a = warp_sum(ra);
+    b = warp_sum(rb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta ; saves mean / rstd per row.
+// ------------------------------------------------------------------------------------------------
+template <int kChunks>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma,
+                                                            const __nv_bfloat16* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int rows, int D, float eps) {
+    __shared__ float red[64];
+    const int nvec = D / 8;
+    const float inv_d = 1.0f / static_cast<float>(D);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * D);
+        uint4 v[kChunks];
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            v[i] = idx < nvec ? xr[idx] : make_uint4(0, 0, 0, 0);
+        }
+        float s = 0.f, dummy = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += f[q];
+        }
+        block_sum2<kLnThreads>(s, dummy, red);
+        const float mean = s * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            if (idx < nvec) {
+                float f[8];
+                unpack8(v[i], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ss += (f[q] - mean) * (f[q] - mean);
+            }
+        }
+        block_sum2<kLnThreads>(ss, dummy, red);
+        const float rstd = rsqrtf(ss * inv_d + eps);
+        if (threadIdx.x == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+        uint4* yr = reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * D);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            if (idx < nvec) {
+                float f[8], g[8], b[8];
+                unpack8(v[i], f);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), g);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + idx), b);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = (f[q] - mean) * rstd * g[q] + b[q];
+                yr[idx] = pack8(f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dx = [dres +] rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; optionally dxsum += sum_rows dx
+// (the latter is the bias gradient of the Linear that produced x's residual branch).
+// ------------------------------------------------------------------------------------------------
+template <int kChunks>
+__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const __nv_bfloat16* __restrict__ dres,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dxsum,
+                                                            int rows, int D) {
+    __shared__ float red[64];
+    const int nvec = D / 8;
+    const float inv_d = 1.0f / static_cast<float>(D);
+    float gam[kChunks][8], dg[kChunks][8], db[kChunks][8], dxs[kChunks][8];
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+        const int idx = threadIdx.x + i * kLnThreads;
+        if (idx < nvec) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), gam[i]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gam[i][q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dg[i][q] = 0.f, db[i][q] = 0.f, dxs[i][q] = 0.f;
+    }
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int64_t base = static_cast<int64_t>(row) * D;
+        const uint4* xr = reinterpret_cast<const uint4*>(x + base);
+        const uint4* dyr = reinterpret_cast<const uint4*>(dy + base);
+        uint4 xv[kChunks], dv[kChunks];
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            xv[i] = idx < nvec ? xr[idx] : make_uint4(0, 0, 0, 0);
+            dv[i] = idx < nvec ? dyr[idx] : make_uint4(0, 0, 0, 0);
+        }
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            if (idx < nvec) {
+                float xf[8], df[8];
+                unpack8(xv[i], xf);
+                unpack8(dv[i], df);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float xhat = (xf[q] - mean) * rstd;
+                    const float g = df[q] * gam[i][q];
+                    s1 += g;
+                    s2 += g * xhat;
+                    dg[i][q] += df[q] * xhat;
+                    db[i][q] += df[q];
+                }
+            }
+        }
+        block_sum2<kLnThreads>(s1, s2, red);
+        s1 *= inv_d;
+        s2 *= inv_d;
+        uint4* dxr = reinterpret_cast<uint4*>(dx + base);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int idx = threadIdx.x + i * kLnThreads;
+            if (idx < nvec) {
+                float xf[8], df[8], rf[8], o[8];
+                unpack8(xv[i], xf);
+                unpack8(dv[i], df);
+                if (dres != nullptr) {
+                    unpack8(reinterpret_cast<const uint4*>(dres + base)[idx], rf);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) rf[q] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float xhat = (xf[q] - mean) * rstd;
+                    o[q] = rf[q] + rstd * (df[q] * gam[i][q] - s1 - xhat * s2);
+                }
+                const uint4 packed = pack8(o);
+                dxr[idx] = packed;
+                if (dxsum != nullptr) {
+                    float ob[8];
+                    unpack8(packed, ob);  // sum what was actually stored (bf16-rounded), like a torch .sum(0)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dxs[i][q] += ob[q];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+        const int idx = threadIdx.x + i * kLnThreads;
+        if (idx < nvec) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                atomicAdd(dgamma + idx * 8 + q, dg[i][q]);
+                atomicAdd(dbeta + idx * 8 + q, db[i][q]);
+                if (dxsum != nullptr) atomicAdd(dxsum + idx * 8 + q, dxs[i][q]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax (attention probabilities), in place on a [rows, ld] bf16 matrix with `n` valid columns.
+// One warp per row; fp32 math; exp2 with pre-multiplied log2(e).
+// ------------------------------------------------------------------------------------------------
+template <int kMaxPairs>  // bf16x2 pairs per lane
+__global__ void softmax_fwd_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int n, int64_t ld, float scale) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    const int lane = threadIdx.x % 32;
+    uint32_t* r = reinterpret_cast<uint32_t*>(s + row * ld);
+    const int npairs = n / 2;
+    const float sl2 = scale * 1.4426950408889634f;
+    float v[kMaxPairs][2];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < npairs) {
+            const uint32_t w = r[idx];
+            v[i][0] = bf16_lo(w) * sl2;
+            v[i][1] = bf16_hi(w) * sl2;
+            mx = fmaxf(mx, fmaxf(v[i][0], v[i][1]));
+        } else {
+            v[i][0] = v[i][1] = -INFINITY;
+        }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+        v[i][0] = exp2f(v[i][0] - mx);
+        v[i][1] = exp2f(v[i][1] - mx);
+        sum += v[i][0] + v[i][1];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < npairs) r[idx] = pack_bf16x2(v[i][0] * inv, v[i][1] * inv);
+    }
+}
+
+// dS = scale * P * (dP - sum_j dP_j P_j), in place on dP.
+template <int kMaxPairs>
+__global__ void softmax_bwd_kernel(__nv_bfloat16* __restrict__ dp, const __nv_bfloat16* __restrict__ p, int64_t rows,
+                                   int n, int64_t ld, float scale) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    const int lane = threadIdx.x % 32;
+    uint32_t* dr = reinterpret_cast<uint32_t*>(dp + row * ld);
+    const uint32_t* pr = reinterpret_cast<const uint32_t*>(p + row * ld);
+    const int npairs = n / 2;
+    float pv[kMaxPairs][2], dv[kMaxPairs][2];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < npairs) {
+            const uint32_t a = pr[idx], b = dr[idx];
+            pv[i][0] = bf16_lo(a), pv[i][1] = bf16_hi(a);
+            dv[i][0] = bf16_lo(b), dv[i][1] = bf16_hi(b);
+            dot += pv[i][0] * dv[i][0] + pv[i][1] * dv[i][1];
+        } else {
+            pv[i][0] = pv[i][1] = dv[i][0] = dv[i][1] = 0.f;
+        }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < npairs)
+            dr[idx] = pack_bf16x2(scale * pv[i][0] * (dv[i][0] - dot), scale * pv[i][1] * (dv[i][1] - dot));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross entropy: loss += mean_b( logsumexp(logits_b) - logits_b[target_b] ), dlogits = (softmax - 1hot)/B
+// One CTA per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cross_entropy_kernel(const __nv_bfloat16* __restrict__ logits,
+                                                            const int64_t* __restrict__ target,
+                                                            __nv_bfloat16* __restrict__ dlogits,
+                                                            float* __restrict__ loss, int* __restrict__ correct,
+                                                            int B, int C, float inv_b) {
+    __shared__ float red[64];
+    __shared__ int red_i[8];
+    const int row = blockIdx.x;
+    const __nv_bfloat16* lr = logits + static_cast<int64_t>(row) * C;
+    float mx = -INFINITY;
+    int arg = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = __bfloat162float(lr[c]);
+        if (v > mx) mx = v, arg = c;
+    }
+    // block arg-max (first index wins on ties, like torch.argmax)
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) mx = om, arg = oa;
+    }
+    const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    if (l == 0) red[w] = mx, red_i[w] = arg;
+    __syncthreads();
+    mx = red[0], arg = red_i[0];
+    for (int i = 1; i < blockDim.x / 32; ++i)
+        if (red[i] > mx || (red[i] == mx && red_i[i] < arg)) mx = red[i], arg = red_i[i];
+    float s = 0.f, dummy = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s += __expf(__bfloat162float(lr[c]) - mx);
+    block_sum2<256>(s, dummy, red);
+    const float lse = mx + __logf(s);
+    const int tgt = static_cast<int>(target[row]);
+    if (dlogits != nullptr) {
+        __nv_bfloat16* dr = dlogits + static_cast<int64_t>(row) * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float pr = __expf(__bfloat162float(lr[c]) - lse);
+            dr[c] = __float2bfloat16((pr - (c == tgt ? 1.f : 0.f)) * inv_b);
+        }
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(loss, (lse - __bfloat162float(lr[tgt])) * inv_b);
+        if (correct != nullptr && arg == tgt) atomicAdd(correct, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch im2col: images [B, 3, S, S] (fp32 or bf16) -> cols [B * (S/P)^2, Kpad] bf16 with
+// k = c * P * P + py * P + px (the Conv2d weight's flattening order); columns >= 3 P^2 are zero.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ cols, int B, int S, int P,
+                              int Kpad) {
+    const int G = S / P;
+    const int64_t total = static_cast<int64_t>(B) * G * G * Kpad;
+    const int K = 3 * P * P;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kpad);
+        const int64_t patch = i / Kpad;
+        float v = 0.f;
+        if (k < K) {
+            const int c = k / (P * P), rem = k % (P * P), py = rem / P, px = rem % P;
+            const int gx = static_cast<int>(patch % G), gy = static_cast<int>((patch / G) % G);
+            const int64_t b = patch / (G * G);
+            v = static_cast<float>(img[((b * 3 + c) * S + gy * P + py) * S + gx * P + px]);
+        }
+        cols[i] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of a [rows, C] bf16 matrix into fp32 (bias gradients that are not fused elsewhere).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                     int64_t rows, int C, int rows_per_cta) {
+    // blockIdx.x: 8-column vector group of 256 threads' worth (256 * 8 columns), blockIdx.y: row slab
+    const int vec = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec * 8 >= C) return;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = r0; r < r1; ++r) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + r * C + vec * 8), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(out + vec * 8 + q, acc[q]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sum of squares (fp32 or bf16 input) -> atomicAdd into one float. Used for the global grad norm.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ out) {
+    __shared__ float red[64];
+    float s = 0.f, dummy = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float v = static_cast<float>(x[i]);
+        s += v * v;
+    }
+    block_sum2<256>(s, dummy, red);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused sharded AdamW.  One pass over the shard:
+//   g   = grad * clip_coef (device scalar; 1.0 when clipping is off)
+//   m,v = Adam moments (fp32)
+//   w   = w * (1 - lr * wd) - lr * mhat / (sqrt(vhat) + eps)          (decoupled weight decay)
+// The fp32 master weight is stored *split*: `hi` is the round-to-nearest bf16 value (this is the
+// tensor the next all-gather ships and the GEMMs consume), `lo` is the signed 16-bit remainder so that
+// (hi << 16) + lo reproduces the fp32 bits exactly.  No separate bf16 copy, no extra cast pass.
+// ------------------------------------------------------------------------------------------------
+template <typename GradT>
+__global__ void __launch_bounds__(256) adamw_split_kernel(uint16_t* __restrict__ hi, int16_t* __restrict__ lo,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          const GradT* __restrict__ grad, int64_t n,
+                                                          const float* __restrict__ clip_coef, float lr, float beta1,
+                                                          float beta2, float eps, float wd, float bc1, float bc2) {
+    const float coef = clip_coef != nullptr ? *clip_coef : 1.0f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int32_t bits = (static_cast<int32_t>(hi[i]) << 16) + static_cast<int32_t>(lo[i]);
+        float w = __int_as_float(bits);
+        const float g = static_cast<float>(grad[i]) * coef;
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        const float mhat = mi / bc1;
+        const float vhat = vi / bc2;
+        w = w * (1.f - lr * wd) - lr * mhat / (sqrtf(vhat) + eps);
+        const int32_t nb = __float_as_int(w);
+        // round-to-nearest-even bf16 in integer arithmetic (weights are finite)
+        const int32_t rounded = nb + 0x7FFF + ((nb >> 16) & 1);
+        const int32_t h = rounded >> 16;
+        hi[i] = static_cast<uint16_t>(h & 0xFFFF);
+        lo[i] = static_cast<int16_t>(nb - (h << 16));
+    }
+}
+
+// Plain fp32-master variant (used when the compute dtype is fp32).
+template <typename GradT>
+__global__ void __launch_bounds__(256) adamw_fp32_kernel(float* __restrict__ w, float* __restrict__ m,
+                                                         float* __restrict__ v, const GradT* __restrict__ grad,
+                                                         int64_t n, const float* __restrict__ clip_coef, float lr,
+                                                         float beta1, float beta2, float eps, float wd, float bc1,
+                                                         float bc2) {
+    const float coef = clip_coef != nullptr ? *clip_coef : 1.0f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float g = static_cast<float>(grad[i]) * coef;
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] = w[i] * (1.f - lr * wd) - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    }
+}
+
+// Split an fp32 tensor into (hi bf16, lo int16) and back.
+__global__ void split_fp32_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, int16_t* __restrict__ lo,
+                                  int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int32_t nb = __float_as_int(w[i]);
+        const int32_t rounded = nb + 0x7FFF + ((nb >> 16) & 1);
+        const int32_t h = rounded >> 16;
+        hi[i] = static_cast<uint16_t>(h & 0xFFFF);
+        lo[i] = static_cast<int16_t>(nb - (h << 16));
+    }
+}
+__global__ void merge_fp32_kernel(const uint16_t* __restrict__ hi, const int16_t* __restrict__ lo,
+                                  float* __restrict__ w, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        w[i] = __int_as_float((static_cast<int32_t>(hi[i]) << 16) + static_cast<int32_t>(lo[i]));
+    }
+}
+
+// clip_coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)); also publishes the norm.
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef,
+                                 float* __restrict__ norm_out) {
+    const float norm = sqrtf(*sumsq);
+    if (norm_out != nullptr) *norm_out = norm;
+    *coef = fminf(1.0f, max_norm / (norm + 1e-6f));
+}
+
+inline void check_launch(const char* what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(err));
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+}  // namespace
+
+#define LN_DISPATCH(CH, KERNEL, ...)                                       \
+    switch (CH) {                                                          \
+        case 1: KERNEL<1><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__); break; \
+        case 2: KERNEL<2><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__); break; \
+        case 3: KERNEL<3><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__); break; \
+        case 4: KERNEL<4><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__); break; \
+        default: throw std::runtime_error("layernorm: width > 8192 not supported"); \
+    }
+
+void layernorm_fwd(const __nv_bfloat16* x, const __nv_bfloat16* gamma, const __nv_bfloat16* beta, __nv_bfloat16* y,
+                   float* mean, float* rstd, int rows, int D, float eps, cudaStream_t stream) {
+    if (D % 8 != 0) throw std::runtime_error("layernorm: width must be a multiple of 8");
+    const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
+    const int grid = std::min(rows, sm_count() * 8);
+    LN_DISPATCH(chunks, ln_fwd_kernel, x, gamma, beta, y, mean, rstd, rows, D, eps);
+    check_launch("layernorm_fwd");
+}
+
+void layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const __nv_bfloat16* gamma, const float* mean,
+                   const float* rstd, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                   float* dxsum, int rows, int D, cudaStream_t stream) {
+    if (D % 8 != 0) throw std::runtime_error("layernorm: width must be a multiple of 8");
+    const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
+    const int grid = std::min(rows, sm_count() * 2);
+    LN_DISPATCH(chunks, ln_bwd_kernel, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D);
+    check_launch("layernorm_bwd");
+}
+
+#define SM_DISPATCH(KERNEL, ...)                                                                   \
+    if (pairs_per_lane <= 2) KERNEL<2><<<grid, 256, 0, stream>>>(__VA_ARGS__);                     \
+    else if (pairs_per_lane <= 4) KERNEL<4><<<grid, 256, 0, stream>>>(__VA_ARGS__);                \
+    else if (pairs_per_lane <= 9) KERNEL<9><<<grid, 256, 0, stream>>>(__VA_ARGS__);                \
+    else if (pairs_per_lane <= 16) KERNEL<16><<<grid, 256, 0, stream>>>(__VA_ARGS__);              \
+    else throw std::runtime_error("softmax: row length > 1024 not supported");
+
+void softmax_fwd(__nv_bfloat16* s, int64_t rows, int n, int64_t ld, float scale, cudaStream_t stream) {
+    if (n % 2 != 0 || ld % 2 != 0) throw std::runtime_error("softmax: row length and ld must be even");
+    const int pairs_per_lane = (n / 2 + 31) / 32;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    SM_DISPATCH(softmax_fwd_kernel, s, rows, n, ld, scale);
+    check_launch("softmax_fwd");
+}
+
+void softmax_bwd(__nv_bfloat16* dp, const __nv_bfloat16* p, int64_t rows, int n, int64_t ld, float scale,
+                 cudaStream_t stream) {
+    if (n % 2 != 0 || ld % 2 != 0) throw std::runtime_error("softmax: row length and ld must be even");
+    const int pairs_per_lane = (n / 2 + 31) / 32;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    SM_DISPATCH(softmax_bwd_kernel, dp, p, rows, n, ld, scale);
+    check_launch("softmax_bwd");
+}
+
+void cross_entropy(const __nv_bfloat16* logits, const int64_t* target, __nv_bfloat16* dlogits, float* loss,
+                   int* correct, int B, int C, cudaStream_t stream) {
+    cross_entropy_kernel<<<B, 256, 0, stream>>>(logits, target, dlogits, loss, correct, B, C, 1.0f / B);
+    check_launch("cross_entropy");
+}
+
+void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S, int P, int Kpad,
+            cudaStream_t stream) {
+    const int grid = sm_count() * 8;
+    if (img_is_bf16)
+        im2col_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(img), cols, B, S, P, Kpad);
+    else
+        im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(img), cols, B, S, P, Kpad);
+    check_launch("im2col");
+}
+
+void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream) {
+    if (C % 8 != 0) throw std::runtime_error("colsum: width must be a multiple of 8");
+    const int gx = (C / 8 + 255) / 256;
+    int slabs = std::max(1, (sm_count() * 4) / gx);
+    int rows_per = static_cast<int>((rows + slabs - 1) / slabs);
+    if (rows_per < 1) rows_per = 1;
+    slabs = static_cast<int>((rows + rows_per - 1) / rows_per);
+    colsum_kernel<<<dim3(gx, slabs), 256, 0, stream>>>(x, out, rows, C, rows_per);
+    check_launch("colsum");
+}
+
+void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stream) {
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 8));
+    if (grid == 0) return;
+    if (is_bf16)
+        sumsq_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), n, out);
+    else
+        sumsq_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), n, out);
+    check_launch("sumsq");
+}
+
+void adamw_split(uint16_t* hi, int16_t* lo, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n,
+                 const float* clip_coef, float lr, float beta1, float beta2, float eps, float wd, int step,
+                 cudaStream_t stream) {
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    if (grad_is_bf16)
+        adamw_split_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(hi, lo, m, v, static_cast<const __nv_bfloat16*>(grad),
+                                                                   n, clip_coef, lr, beta1, beta2, eps, wd, bc1, bc2);
+    else
+        adamw_split_kernel<float><<<grid, 256, 0, stream>>>(hi, lo, m, v, static_cast<const float*>(grad), n, clip_coef,
+                                                           lr, beta1, beta2, eps, wd, bc1, bc2);
+    check_launch("adamw_split");
+}
+
+void adamw_fp32(float* w, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n, const float* clip_coef,
+                float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t stream) {
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    if (grad_is_bf16)
+        adamw_fp32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, m, v, static_cast<const __nv_bfloat16*>(grad), n,
+                                                                  clip_coef, lr, beta1, beta2, eps, wd, bc1, bc2);
+    else
+        adamw_fp32_kernel<float><<<grid, 256, 0, stream>>>(w, m, v, static_cast<const float*>(grad), n, clip_coef, lr,
+                                                          beta1, beta2, eps, wd, bc1, bc2);
+    check_launch("adamw_fp32");
+}
+
+void split_fp32(const float* w, uint16_t* hi, int16_t* lo, int64_t n, cudaStream_t stream) {
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    split_fp32_kernel<<<grid, 256, 0, stream>>>(w, hi, lo, n);
+    check_launch("split_fp32");
+}
+
+void merge_fp32(const uint16_t* hi, const int16_t* lo, float* w, int64_t n, cudaStream_t stream) {
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    merge_fp32_kernel<<<grid, 256, 0, stream>>>(hi, lo, w, n);
+    check_launch("merge_fp32");
+}
+
+void clip_coef(const float* sumsq_in, float max_norm, float* coef, float* norm_out, cudaStream_t stream) {
+    clip_coef_kernel<<<1, 1, 0, stream>>>(sumsq_in, max_norm, coef, norm_out);
+    check_launch("clip_coef");
+}
+
+}  // namespace b200

@@ -1,0 +1,550 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a (B200):
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B)  ->  shared-memory ring
+//   tcgen05.mma.cta_group::2 (UMMA 256 x BLOCK_N x 16, one elected thread of the leader CTA)
+//   fp32 accumulators double-buffered in TMEM  ->  tcgen05.ld epilogue warps
+//   fused epilogue (bias, exact GELU, dGELU, residual add, pre-activation side output,
+//   bias-gradient column sums)  ->  swizzled smem  ->  TMA store.
+//
+// One CTA pair (thread-block cluster of 2 = one TPC) owns a 256 x BLOCK_N output tile; each CTA
+// loads its own 128 rows of A and half of the B tile, so every operand byte is fetched once per pair.
+//
+//   D[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] )
+//
+// A and B may each be K-major (reduction dim contiguous) or MN-major (reduction dim strided), which
+// covers forward (NT), dgrad (NN) and wgrad (TN) without materialising transposes.  Operands are 4-D
+// TMA tensors (inner, outer, batch_inner, batch_outer) so strided per-head attention operands inside a
+// packed qkv buffer are addressed in place.
+//
+// Capability parity: replaces the XLA-lowered dot ops under timm's Linear layers that the reference
+// calls at run_vit_training.py:134-141,153 (qkv / proj / fc1 / fc2 / head) and their autograd
+// backward.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+
+#include "gemm_sm100.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kBlockM = 128;  // rows per CTA (cluster tile = 256)
+constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kCdBufs = 4;             // ring of 128x64 bf16 staging buffers for TMA stores
+constexpr int kCdBufBytes = 128 * 128;  // 128 rows x 128 B
+
+struct KernelParams {
+    int M, N, K;
+    int batch, nb_inner;
+    int m_tiles, n_tiles;  // cluster tiles (256 x BLOCK_N)
+    GemmEpilogue epi;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+template <int kMajorA, int kMajorB, int BLOCK_N, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+    gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                           const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_aux,
+                           const KernelParams p) {
+    constexpr int LOAD_N = BLOCK_N / 2;  // B rows loaded per CTA
+    constexpr int kABytes = kBlockM * kBlockK * 2;
+    constexpr int kBBytes = LOAD_N * kBlockK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kTmemCols = (2 * BLOCK_N <= 32)    ? 32
+                              : (2 * BLOCK_N <= 64)  ? 64
+                              : (2 * BLOCK_N <= 128) ? 128
+                              : (2 * BLOCK_N <= 256) ? 256
+                                                     : 512;
+    static_assert(2 * BLOCK_N <= 512, "accumulator double buffer must fit TMEM");
+    static_assert(BLOCK_N % 64 == 0, "epilogue works in 64-column chunks");
+    static_assert(kMajorB == 0 || LOAD_N % 64 == 0, "MN-major B needs whole 64-wide atoms per CTA");
+    static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle-128B needs 1024 B aligned stages");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_cd = smem;
+    uint8_t* smem_a = smem + kCdBufs * kCdBufBytes;
+    uint8_t* smem_b = smem_a + kStages * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kBBytes);
+    uint64_t* full_bar = bars;                     // [kStages]   TMA -> MMA   (leader CTA's copy is used)
+    uint64_t* empty_bar = bars + kStages;          // [kStages]   MMA -> TMA   (both CTAs)
+    uint64_t* tmem_full_bar = bars + 2 * kStages;  // [2]         MMA -> epilogue (both CTAs)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]         epilogue -> MMA (leader CTA's copy)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const uint32_t warp_idx = threadIdx.x / 32;
+    const uint32_t lane = lane_id();
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+
+    if (warp_idx == 0 && elect_one()) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_d);
+        if (p.epi.has_aux_out) prefetch_tmap(&tmap_aux);
+    }
+    if (warp_idx == 1 && elect_one()) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 2);   // leader's expect_tx arrive + peer's plain arrive
+            mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);   // one multicast tcgen05.commit
+            mbar_init(&tmem_empty_bar[i], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        fence_mbar_init();
+    }
+    cluster_sync();  // barriers visible cluster-wide before anyone touches a peer's barrier / TMEM alloc
+    if (warp_idx == 2) tmem_alloc<2>(tmem_ptr_smem, kTmemCols);
+    tc_fence_before();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_clusters = gridDim.x / 2;
+    const int cluster_id = blockIdx.x / 2;
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_per_batch * p.batch;
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    constexpr int kGroupN = 8;  // n-tiles per raster group (keeps a wave's A/B footprint L2-resident)
+
+    auto decode_tile = [&](int t, int& b, int& mt, int& nt) {
+        b = t / tiles_per_batch;
+        const int r = t - b * tiles_per_batch;
+        const int per_group = p.m_tiles * kGroupN;
+        const int g = r / per_group;
+        const int first_n = g * kGroupN;
+        const int gsz = min(kGroupN, p.n_tiles - first_n);
+        const int in_g = r - g * per_group;
+        mt = in_g / gsz;
+        nt = first_n + in_g % gsz;
+    };
+
+    if (warp_idx == 0) {
+        // ================================= TMA producer =================================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                int b, mt, nt;
+                decode_tile(t, b, mt, nt);
+                const int bi = b % p.nb_inner, bo = b / p.nb_inner;
+                const int m_idx = mt * (2 * kBlockM) + cta_rank * kBlockM;
+                const int n_idx = nt * BLOCK_N + cta_rank * LOAD_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const int k_idx = kb * kBlockK;
+                    uint8_t* sa = smem_a + stage * kABytes;
+                    uint8_t* sb = smem_b + stage * kBBytes;
+                    if constexpr (kMajorA == 0) {
+                        tma_load_4d_2cta(&tmap_a, &full_bar[stage], sa, k_idx, m_idx, bi, bo);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kBlockM / 64; ++i)
+                            tma_load_4d_2cta(&tmap_a, &full_bar[stage], sa + i * (64 * kBlockK * 2), m_idx + i * 64,
+                                             k_idx, bi, bo);
+                    }
+                    if constexpr (kMajorB == 0) {
+                        tma_load_4d_2cta(&tmap_b, &full_bar[stage], sb, k_idx, n_idx, bi, bo);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < LOAD_N / 64; ++i)
+                            tma_load_4d_2cta(&tmap_b, &full_bar[stage], sb + i * (64 * kBlockK * 2), n_idx + i * 64,
+                                             k_idx, bi, bo);
+                    }
+                    if (is_leader) {
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                    } else {
+                        mbar_arrive_cluster(&full_bar[stage], 0);
+                    }
+                    stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                    phase ^= (stage == 0);
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ================================= MMA issuer (leader CTA only) =================================
+        if (is_leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BLOCK_N, kMajorA, kMajorB);
+            // K-major : 8-row groups are 1024 B apart (SBO); one swizzle atom along K so LBO unused.
+            // MN-major: 8-k groups are 1024 B apart (SBO); 64-wide MN atoms are BLOCK_K*128 B apart (LBO).
+            constexpr uint32_t kLboA = kMajorA == 0 ? 0 : kBlockK * 128;
+            constexpr uint32_t kLboB = kMajorB == 0 ? 0 : kBlockK * 128;
+            constexpr uint32_t kKStepA = kMajorA == 0 ? (kUmmaK * 2) : (kUmmaK * 128);  // bytes per UMMA_K
+            constexpr uint32_t kKStepB = kMajorB == 0 ? (kUmmaK * 2) : (kUmmaK * 128);
+            uint32_t stage = 0, phase = 0;
+            uint32_t iter = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
+                const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t da = make_smem_desc_sw128(a_addr + k * kKStepA, kLboA, 1024);
+                            const uint64_t db = make_smem_desc_sw128(b_addr + k * kKStepB, kLboB, 1024);
+                            umma_bf16<2>(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit<2>(&empty_bar[stage]);  // frees the smem slot in both CTAs
+                        if (kb == num_kb - 1) umma_commit<2>(&tmem_full_bar[as]);
+                    }
+                    __syncwarp();
+                    stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                    phase ^= (stage == 0);
+                }
+            }
+            // Drain: make sure every epilogue (both CTAs) released the last accumulators before teardown.
+            if (iter > 0) {
+                const uint32_t last = iter - 1;
+                mbar_wait(&tmem_empty_bar[last & 1], (last >> 1) & 1);
+                if (iter > 1) {
+                    const uint32_t prev = iter - 2;
+                    mbar_wait(&tmem_empty_bar[prev & 1], (prev >> 1) & 1);
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ================================= Epilogue warps =================================
+        const uint32_t ew = warp_idx - 4;              // == warp_idx % 4: TMEM lane quarter of this warp
+        const uint32_t etid = threadIdx.x - 128;       // 0..127
+        const uint32_t row_in_tile = ew * 32 + lane;   // accumulator row owned by this thread
+        const GemmEpilogue& e = p.epi;
+        uint32_t iter = 0;
+        uint32_t cd_idx = 0;  // ring position (identical on all epilogue threads)
+        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++iter) {
+            int b, mt, nt;
+            decode_tile(t, b, mt, nt);
+            const int bi = b % p.nb_inner, bo = b / p.nb_inner;
+            const int m0 = mt * (2 * kBlockM) + cta_rank * kBlockM;
+            const int n0 = nt * BLOCK_N;
+            const int row = m0 + row_in_tile;
+            const bool row_ok = row < p.M;
+            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((ew * 32) << 16) + as * BLOCK_N;
+
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+                const int ncol0 = n0 + c * 64;
+                uint32_t acc_lo[32], acc_hi[32];
+                tmem_ld_32x32b_x32(taddr + c * 64, acc_lo);
+                tmem_ld_32x32b_x32(taddr + c * 64 + 32, acc_hi);
+                tmem_ld_wait();
+                if (c == BLOCK_N / 64 - 1) {
+                    // accumulators are in registers: hand the TMEM stage back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                }
+                if (ncol0 >= p.N) continue;  // tile-uniform: whole chunk is out of range (nothing to store)
+
+                // ---- fused math, 8 columns (one 16 B bf16 vector) at a time ----
+                uint32_t out[32];  // 64 bf16 packed
+                uint32_t pre[32];  // pre-activation side output (only if has_aux_out)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = ncol0 + j * 8;
+                    const bool col_ok = col < p.N;
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = j * 8 + q;
+                        v[q] = __uint_as_float(idx < 32 ? acc_lo[idx] : acc_hi[idx - 32]);
+                    }
+                    if (e.bias != nullptr && col_ok) {
+                        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(e.bias + col));
+                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[2 * q] += bf16_lo(bw[q]);
+                            v[2 * q + 1] += bf16_hi(bw[q]);
+                        }
+                    }
+                    if (e.has_aux_out) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) pre[j * 4 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                    }
+                    if (e.act == kActGelu) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = gelu_erf(v[q]);
+                    } else if (e.act == kActDGelu) {
+                        uint4 uv = make_uint4(0, 0, 0, 0);
+                        if (row_ok && col_ok)
+                            uv = *reinterpret_cast<const uint4*>(e.aux_in + static_cast<int64_t>(row) * e.ld_aux + col);
+                        const uint32_t uw[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[2 * q] *= dgelu_erf(bf16_lo(uw[q]));
+                            v[2 * q + 1] *= dgelu_erf(bf16_hi(uw[q]));
+                        }
+                    }
+                    if (e.residual != nullptr) {
+                        uint4 rv = make_uint4(0, 0, 0, 0);
+                        if (row_ok && col_ok) {
+                            const int rrow = e.res_row_mod > 0 ? row % e.res_row_mod : row;
+                            rv = *reinterpret_cast<const uint4*>(e.residual + static_cast<int64_t>(rrow) * e.ld_res + col);
+                        }
+                        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[2 * q] += bf16_lo(rw[q]);
+                            v[2 * q + 1] += bf16_hi(rw[q]);
+                        }
+                    }
+                    if (!(row_ok && col_ok)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = 0.f;  // keeps the column sums clean
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) out[j * 4 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                }
+
+                // ---- stage through swizzled smem and TMA-store ----
+                const int n_stores = e.has_aux_out ? 2 : 1;
+                if (etid == 0) {
+                    if (e.has_aux_out)
+                        tma_store_wait_read<kCdBufs - 2>();
+                    else
+                        tma_store_wait_read<kCdBufs - 1>();
+                }
+                named_bar_sync(1, kEpiThreads);
+                uint8_t* buf0 = smem_cd + (cd_idx % kCdBufs) * kCdBufBytes;
+                uint8_t* buf1 = smem_cd + ((cd_idx + 1) % kCdBufs) * kCdBufBytes;
+                {
+                    const uint32_t rbase = smem_u32(buf0) + row_in_tile * 128;
+                    const uint32_t rbase1 = smem_u32(buf1) + row_in_tile * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t off = ((j ^ (row_in_tile & 7)) * 16);
+                        st_shared_v4(rbase + off, out[j * 4], out[j * 4 + 1], out[j * 4 + 2], out[j * 4 + 3]);
+                        if (e.has_aux_out)
+                            st_shared_v4(rbase1 + off, pre[j * 4], pre[j * 4 + 1], pre[j * 4 + 2], pre[j * 4 + 3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, kEpiThreads);
+                if (etid == 0) {
+                    tma_store_4d(&tmap_d, buf0, ncol0, m0, bi, bo);
+                    tma_store_commit();
+                    if (e.has_aux_out) {
+                        tma_store_4d(&tmap_aux, buf1, ncol0, m0, bi, bo);
+                        tma_store_commit();
+                    }
+                }
+                if (e.colsum != nullptr) {
+                    // Bias gradient: column sums of the (bf16-rounded) output tile, fp32 atomics.
+                    const int ccol = etid & 63;       // column within the chunk
+                    const int rhalf = etid >> 6;      // 0/1 -> rows [0,64) / [64,128)
+                    const int jj = ccol >> 3, within = ccol & 7;
+                    float s = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < 64; ++r) {
+                        const int rr = rhalf * 64 + r;
+                        const uint8_t* ptr = buf0 + rr * 128 + ((jj ^ (rr & 7)) * 16) + within * 2;
+                        s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ptr));
+                    }
+                    if (ncol0 + ccol < p.N)
+                        atomicAdd(e.colsum + static_cast<int64_t>(bi) * e.colsum_bi_stride + ncol0 + ccol, s);
+                }
+                cd_idx += n_stores;
+            }
+        }
+        if (etid == 0) tma_store_wait<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync();
+    if (warp_idx == 2) tmem_dealloc<2>(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+        if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr)
+            throw std::runtime_error("cuTensorMapEncodeTiled not available from the driver");
+        fn = reinterpret_cast<EncodeFn>(sym);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    uint64_t ptr;
+    int64_t d[4];
+    int64_t s[3];
+    int32_t box[2];
+    bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        size_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+        return h;
+    }
+};
+
+// 4-D bf16 tensor map: dims (inner, outer, batch_inner, batch_outer), box (box_inner, box_outer, 1, 1).
+CUtensorMap make_tmap(const GemmOperand& op, int64_t inner, int64_t outer, int box_inner, int box_outer) {
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    static std::mutex mu;
+    TmapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.ptr = reinterpret_cast<uint64_t>(op.ptr);
+    key.d[0] = inner, key.d[1] = outer, key.d[2] = op.nb_inner, key.d[3] = op.nb_outer;
+    key.s[0] = op.ld, key.s[1] = op.stride_b_inner, key.s[2] = op.stride_b_outer;
+    key.box[0] = box_inner, key.box[1] = box_outer;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    if ((reinterpret_cast<uint64_t>(op.ptr) & 15) != 0) throw std::runtime_error("gemm: operand base must be 16 B aligned");
+    if ((op.ld * 2) % 16 != 0) throw std::runtime_error("gemm: leading dimension must be a multiple of 8 elements");
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer),
+                          static_cast<cuuint64_t>(op.nb_inner), static_cast<cuuint64_t>(op.nb_outer)};
+    // Strides of size-1 batch dims are irrelevant but must still be legal multiples of 16 B.
+    const int64_t sbi = op.nb_inner > 1 ? op.stride_b_inner : op.ld * outer;
+    const int64_t sbo = op.nb_outer > 1 ? op.stride_b_outer : sbi * op.nb_inner;
+    if ((sbi * 2) % 16 != 0 || (sbo * 2) % 16 != 0) throw std::runtime_error("gemm: batch strides must be multiples of 8 elements");
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(op.ld * 2), static_cast<cuuint64_t>(sbi * 2),
+                             static_cast<cuuint64_t>(sbo * 2)};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult res = get_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) {
+        char msg[256];
+        snprintf(msg, sizeof(msg),
+                 "cuTensorMapEncodeTiled failed (%d): dims=(%lld,%lld,%lld,%lld) ld=%lld box=(%d,%d)", (int)res,
+                 (long long)inner, (long long)outer, (long long)op.nb_inner, (long long)op.nb_outer, (long long)op.ld,
+                 box_inner, box_outer);
+        throw std::runtime_error(msg);
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, tm);
+    return tm;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int kMajorA, int kMajorB, int BLOCK_N, int kStages>
+void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, const GemmOperand* aux, int M, int N,
+            int K, const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
+    constexpr int LOAD_N = BLOCK_N / 2;
+    constexpr int kSmem = kCdBufs * kCdBufBytes + kStages * (kBlockM * kBlockK * 2 + LOAD_N * kBlockK * 2) +
+                          (2 * kStages + 4) * 8 + 16;
+    static_assert(kSmem <= 232448, "shared memory budget exceeded");
+    auto kern = gemm_bf16_sm100_kernel<kMajorA, kMajorB, BLOCK_N, kStages>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+        attr_set = true;
+    }
+    // A: K-major -> (inner=K, outer=M), box (64, 128).  MN-major -> (inner=M, outer=K), box (64, 64).
+    CUtensorMap ta = kMajorA == 0 ? make_tmap(A, K, M, kBlockK, kBlockM) : make_tmap(A, M, K, 64, kBlockK);
+    CUtensorMap tb = kMajorB == 0 ? make_tmap(B, K, N, kBlockK, LOAD_N) : make_tmap(B, N, K, 64, kBlockK);
+    CUtensorMap td = make_tmap(D, N, M, 64, kBlockM);
+    CUtensorMap tx = (epi.has_aux_out && aux != nullptr) ? make_tmap(*aux, N, M, 64, kBlockM) : td;
+
+    KernelParams p;
+    p.M = M, p.N = N, p.K = K;
+    p.batch = static_cast<int>(D.nb_inner * D.nb_outer);
+    p.nb_inner = static_cast<int>(D.nb_inner);
+    p.m_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+    p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    p.epi = epi;
+    const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.batch;
+    int sms = num_sms();
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    int clusters = static_cast<int>(std::min<int64_t>(total, sms / 2));
+    if (clusters < 1) clusters = 1;
+
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(kNumThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, p);
+    if (err != cudaSuccess) throw std::runtime_error(std::string("gemm launch failed: ") + cudaGetErrorString(err));
+}
+
+}  // namespace
+
+void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
+               const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
+               cudaStream_t stream) {
+    if (N % 8 != 0) throw std::runtime_error("gemm: N must be a multiple of 8");
+    if (D.nb_inner * D.nb_outer > 1 && (epi.bias || epi.residual || epi.aux_in))
+        throw std::runtime_error("gemm: bias/residual/aux_in are not supported for batched problems");
+    if (block_n == 0) block_n = (N > 128) ? 256 : 128;
+#define B200_DISPATCH(MA, MB, BN, ST)                                                             \
+    if (major_a == MA && major_b == MB && block_n == BN) {                                        \
+        launch<MA, MB, BN, ST>(A, B, D, aux_out, M, N, K, epi, max_ctas, stream);                 \
+        return;                                                                                   \
+    }
+    B200_DISPATCH(0, 0, 256, 5)
+    B200_DISPATCH(0, 1, 256, 5)
+    B200_DISPATCH(1, 1, 256, 5)
+    B200_DISPATCH(1, 0, 256, 5)
+    B200_DISPATCH(0, 0, 128, 6)
+    B200_DISPATCH(0, 1, 128, 6)
+    B200_DISPATCH(1, 1, 128, 6)
+    B200_DISPATCH(1, 0, 128, 6)
+#undef B200_DISPATCH
+    throw std::runtime_error("gemm: unsupported (major_a, major_b, block_n) combination");
+}
+
+}  // namespace b200

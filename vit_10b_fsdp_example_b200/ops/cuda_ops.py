@@ -1,0 +1,218 @@
+"""sm_100a implementation of the functional op set (same contract as ``torch_ops``).
+
+Every function launches hand-written kernels from ``_C.so``:
+  * GEMMs: persistent 2-CTA tcgen05 kernel with TMEM accumulators and fused epilogues
+    (bias / GELU / dGELU / residual / pre-activation side output / bias-gradient column sums);
+    forward (NT), dgrad (NN) and wgrad (TN) run on the same kernel via K-major / MN-major descriptors.
+  * attention core: batched tcgen05 GEMMs that read q/k/v in place from the packed qkv buffer through
+    4-D TMA tensor maps + a fused scale/softmax kernel (fwd) and softmax-backward kernel (bwd).
+  * LayerNorm fwd/bwd, cross-entropy, im2col, column sums, sum of squares, fused AdamW.
+
+bf16 activations / weights, fp32 accumulation and statistics.  There is no PyTorch fallback here: if the
+extension is missing this module fails to import on purpose.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native, torch_ops
+
+NAME = "sm100"
+_C = native.load()
+
+ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+
+# SM carve-out for compute kernels while a communication kernel runs next to them (0 = all SMs).
+_max_ctas = 0
+
+
+def set_compute_max_ctas(n: int) -> None:
+    global _max_ctas
+    _max_ctas = int(n)
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D (possibly strided) matrix"
+    return t.stride(0)
+
+
+def gemm_raw(a, lda, major_a, b, ldb, major_b, d, ldd, M, N, K, *, bias=None, residual=None, ld_res=0,
+             res_row_mod=0, aux_in=None, ld_aux=0, aux_out=None, ld_aux_out=0, colsum=None, colsum_bi_stride=0,
+             act=ACT_NONE, batch=(), block_n=0, max_ctas=None):
+    _C.gemm(a, lda, major_a, b, ldb, major_b, d, ldd, M, N, K, bias, residual, ld_res, res_row_mod, aux_in, ld_aux,
+            aux_out, ld_aux_out, colsum, colsum_bi_stride, act, list(batch), block_n,
+            _max_ctas if max_ctas is None else max_ctas)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def ln_fwd(x, w, b, eps: float):
+    rows = x.shape[0]
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _C.layernorm_fwd(x, w, b, y, mean, rstd, eps)
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, w, mean, rstd, dres=None, want_dxsum: bool = False):
+    D = x.shape[1]
+    dx = torch.empty_like(x)
+    acc = torch.zeros(3 if want_dxsum else 2, D, dtype=torch.float32, device=x.device)
+    _C.layernorm_bwd(dy, x, w, mean, rstd, dres, dx, acc[0], acc[1], acc[2] if want_dxsum else None)
+    return dx, acc[0], acc[1], (acc[2] if want_dxsum else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear
+# ------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_row_mod: int = 0,
+               want_preact: bool = False):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    pre = torch.empty(M, N, dtype=x.dtype, device=x.device) if want_preact else None
+    gemm_raw(x, _ld(x), 0, w, _ld(w), 0, y, N, M, N, K, bias=bias, residual=residual,
+             ld_res=_ld(residual) if residual is not None else 0, res_row_mod=res_row_mod, aux_out=pre,
+             ld_aux_out=N, act=ACT_GELU if act == "gelu" else ACT_NONE)
+    return (y, pre) if want_preact else y
+
+
+def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
+    cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if want_colsum else None
+    gemm_raw(dy, _ld(dy), 0, w, _ld(w), 1, dx, K, M, K, N, aux_in=dgelu_preact,
+             ld_aux=_ld(dgelu_preact) if dgelu_preact is not None else 0,
+             act=ACT_DGELU if dgelu_preact is not None else ACT_NONE, colsum=cs)
+    return (dx, cs) if want_colsum else dx
+
+
+def linear_wgrad(dy, x, out=None):
+    T, N = dy.shape
+    K = x.shape[1]
+    if out is None:
+        out = torch.empty(N, K, dtype=dy.dtype, device=dy.device)
+    gemm_raw(dy, _ld(dy), 1, x, _ld(x), 1, out, _ld(out), N, K, T)
+    return out
+
+
+def colsum(x):
+    out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    _C.colsum(x, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention core
+# ------------------------------------------------------------------------------------------------
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0):
+    if drop_mask is not None:  # attention dropout > 0: rare path, run the reference math
+        return torch_ops.attention_fwd(qkv, B, N, H, hd, drop_mask, drop_scale)
+    D = H * hd
+    ldp = _pad8(N)
+    p = torch.empty(B * H, N, ldp, dtype=qkv.dtype, device=qkv.device)
+    if ldp != N:
+        p[:, :, N:].zero_()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    ld3 = qkv.stride(0)
+    # S = Q K^T  (per (image, head) problem; operands addressed in place inside qkv)
+    gemm_raw(q, ld3, 0, k, ld3, 0, p, ldp, N, N, hd,
+             batch=(H, B, hd, N * ld3, hd, N * ld3, N * ldp, H * N * ldp))
+    _C.softmax_fwd(p, B * H * N, N, ldp, hd ** -0.5)
+    out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
+    # O = P V  (V is MN-major: head-dim contiguous, keys strided)
+    gemm_raw(p, ldp, 0, v, ld3, 1, out, D, N, hd, N,
+             batch=(H, B, N * ldp, H * N * ldp, hd, N * ld3, hd, N * D))
+    return out, p
+
+
+def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,
+                  drop_scale: float = 1.0):
+    if drop_mask is not None:
+        return torch_ops.attention_bwd(dout, qkv, p, B, N, H, hd, want_colsum, drop_mask, drop_scale)
+    D = H * hd
+    ldp = p.shape[2]
+    ld3 = qkv.stride(0)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    dqkv = torch.empty(B * N, 3 * D, dtype=qkv.dtype, device=qkv.device)
+    dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+    cs = torch.zeros(3 * D, dtype=torch.float32, device=qkv.device) if want_colsum else None
+    ldo = dout.stride(0)
+    bp = (N * ldp, H * N * ldp)      # batch strides of P-shaped buffers
+    bq = (hd, N * ld3)               # ... of q/k/v inside qkv
+    bo = (hd, N * ldo)
+    bd = (hd, N * 3 * D)             # ... of dq/dk/dv inside dqkv
+    # dV = P^T dO
+    gemm_raw(p, ldp, 1, dout, ldo, 1, dv, 3 * D, N, hd, N, batch=(H, B, *bp, *bo, *bd),
+             colsum=cs[2 * D:] if want_colsum else None, colsum_bi_stride=hd)
+    # dP = dO V^T
+    dp = torch.empty_like(p)
+    if ldp != N:
+        dp[:, :, N:].zero_()
+    gemm_raw(dout, ldo, 0, v, ld3, 0, dp, ldp, N, N, hd, batch=(H, B, *bo, *bq, *bp))
+    # dS = scale * P * (dP - rowsum(dP * P))   (in place)
+    _C.softmax_bwd(dp, p, B * H * N, N, ldp, hd ** -0.5)
+    # dQ = dS K ; dK = dS^T Q
+    gemm_raw(dp, ldp, 0, k, ld3, 1, dq, 3 * D, N, hd, N, batch=(H, B, *bp, *bq, *bd),
+             colsum=cs[:D] if want_colsum else None, colsum_bi_stride=hd)
+    gemm_raw(dp, ldp, 1, q, ld3, 1, dk, 3 * D, N, hd, N, batch=(H, B, *bp, *bq, *bd),
+             colsum=cs[D:2 * D] if want_colsum else None, colsum_bi_stride=hd)
+    return (dqkv, cs) if want_colsum else dqkv
+
+
+# ------------------------------------------------------------------------------------------------
+# Patch embedding, loss
+# ------------------------------------------------------------------------------------------------
+def patch_im2col(images, P: int, kpad: int, dtype):
+    B, _, S, _ = images.shape
+    G = S // P
+    cols = torch.empty(B * G * G, kpad, dtype=dtype, device=images.device)
+    _C.im2col(images.contiguous(), cols, P)
+    return cols
+
+
+def cross_entropy(logits, target, want_grad: bool = True):
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    correct = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    _C.cross_entropy(logits, target, dlogits, loss, correct)
+    return loss[0], dlogits, correct[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Optimizer pieces
+# ------------------------------------------------------------------------------------------------
+def sumsq(x, out):
+    _C.sumsq(x, out)
+
+
+def clip_coef(sumsq_t, max_norm: float):
+    coef = torch.empty(1, dtype=torch.float32, device=sumsq_t.device)
+    norm = torch.empty(1, dtype=torch.float32, device=sumsq_t.device)
+    _C.clip_coef(sumsq_t, max_norm, coef, norm)
+    return coef, norm
+
+
+def adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
+    _C.adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)
+
+
+def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
+    _C.adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)
+
+
+def split_fp32(w, hi, lo):
+    _C.split_fp32(w, hi, lo)
+
+
+def merge_fp32(hi, lo, w):
+    _C.merge_fp32(hi, lo, w)

@@ -1,0 +1,198 @@
+"""Reference implementation of the functional op set in plain PyTorch.
+
+This is (a) the CPU / gloo test backend, (b) the fp32 numerical oracle every sm_100a kernel is tested
+against, and (c) the semantics contract for ``cuda_ops``.  Every function here has a same-named,
+same-signature twin in ``cuda_ops`` that runs the hand-written kernels.
+
+All matrices are 2-D ``[tokens, features]``; the model code does its own reshapes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+NAME = "torch"
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm (timm Block.norm1 / norm2, final norm) -- reference run_vit_training.py:134-141,151
+# ------------------------------------------------------------------------------------------------
+def ln_fwd(x, w, b, eps: float):
+    xf = _f32(x)
+    mean = xf.mean(dim=-1)
+    var = xf.var(dim=-1, unbiased=False)
+    rstd = torch.rsqrt(var + eps)
+    y = (xf - mean[:, None]) * rstd[:, None] * _f32(w) + _f32(b)
+    return y.to(x.dtype), mean, rstd
+
+
+def ln_bwd(dy, x, w, mean, rstd, dres=None, want_dxsum: bool = False):
+    """Returns dx (= dres + LN backward), dw fp32, db fp32, colsum(dx) fp32 or None."""
+    dyf, xf, wf = _f32(dy), _f32(x), _f32(w)
+    xhat = (xf - mean[:, None]) * rstd[:, None]
+    g = dyf * wf
+    s1 = g.mean(dim=-1, keepdim=True)
+    s2 = (g * xhat).mean(dim=-1, keepdim=True)
+    dx = rstd[:, None] * (g - s1 - xhat * s2)
+    if dres is not None:
+        dx = dx + _f32(dres)
+    dw = (dyf * xhat).sum(dim=0)
+    db = dyf.sum(dim=0)
+    dx = dx.to(x.dtype)
+    dxsum = _f32(dx).sum(dim=0) if want_dxsum else None
+    return dx, dw, db, dxsum
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear layers (timm Attention.qkv / proj, Mlp.fc1 / fc2, head) and their backward
+# ------------------------------------------------------------------------------------------------
+def gelu(x):
+    return F.gelu(x)  # exact erf form, like timm's nn.GELU
+
+
+def dgelu(u):
+    uf = _f32(u)
+    cdf = 0.5 * (1.0 + torch.erf(uf * (1.0 / math.sqrt(2.0))))
+    pdf = torch.exp(-0.5 * uf * uf) * (1.0 / math.sqrt(2.0 * math.pi))
+    return cdf + uf * pdf
+
+
+def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_row_mod: int = 0,
+               want_preact: bool = False):
+    """y = act(x @ w.T + bias) + residual.  residual rows may be broadcast with period res_row_mod."""
+    y = _f32(x) @ _f32(w).t()
+    if bias is not None:
+        y = y + _f32(bias)
+    pre = y.to(x.dtype) if want_preact else None
+    if act == "gelu":
+        y = gelu(y)
+    elif act is not None:
+        raise ValueError(act)
+    if residual is not None:
+        r = _f32(residual)
+        if res_row_mod:
+            reps = y.shape[0] // res_row_mod
+            r = r[:res_row_mod].repeat(reps, 1)
+        y = y + r
+    y = y.to(x.dtype)
+    return (y, pre) if want_preact else y
+
+
+def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
+    """dx = dy @ w  (optionally  * gelu'(preact)); colsum(dx) is the bias grad of the layer below."""
+    dx = _f32(dy) @ _f32(w)
+    if dgelu_preact is not None:
+        dx = dx * dgelu(dgelu_preact)
+    dx = dx.to(dy.dtype)
+    cs = _f32(dx).sum(dim=0) if want_colsum else None
+    return (dx, cs) if want_colsum else dx
+
+
+def linear_wgrad(dy, x, out=None):
+    """dw[N, K] = dy[T, N].T @ x[T, K]"""
+    dw = _f32(dy).t() @ _f32(x)
+    if out is not None:
+        out.copy_(dw)
+        return out
+    return dw.to(dy.dtype)
+
+
+def colsum(x):
+    return _f32(x).sum(dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention core (timm Attention: softmax(q k^T * hd^-0.5) v, no mask) -- run_vit_training.py:134
+# qkv is the packed [T, 3*D] projection; head h of q lives at columns [h*hd, (h+1)*hd).
+# ------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0):
+    D = H * hd
+    q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)  # [B, H, N, hd]
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    p = torch.softmax(s, dim=-1).to(qkv.dtype)
+    pd = p
+    if drop_mask is not None:
+        pd = (p * drop_mask * drop_scale).to(qkv.dtype)
+    o = (_f32(pd) @ v).permute(0, 2, 1, 3).reshape(B * N, D).to(qkv.dtype)
+    return o, p
+
+
+def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,
+                  drop_scale: float = 1.0):
+    D = H * hd
+    q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    do = _f32(dout).view(B, N, H, hd).permute(0, 2, 1, 3)  # [B, H, N, hd]
+    pf = _f32(p)
+    pdrop = pf if drop_mask is None else (pf * drop_mask * drop_scale).to(qkv.dtype).float()
+    dv = pdrop.transpose(-1, -2) @ do
+    dp = (do @ v.transpose(-1, -2)).to(qkv.dtype).float()
+    if drop_mask is not None:
+        dp = dp * drop_mask * drop_scale
+    ds = (hd ** -0.5) * pf * (dp - (dp * pf).sum(dim=-1, keepdim=True))
+    ds = ds.to(qkv.dtype).float()
+    dq = ds @ k
+    dk = ds.transpose(-1, -2) @ q
+    dqkv = torch.stack([dq, dk, dv], dim=0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D).to(qkv.dtype)
+    cs = _f32(dqkv).sum(dim=0) if want_colsum else None
+    return (dqkv, cs) if want_colsum else dqkv
+
+
+# ------------------------------------------------------------------------------------------------
+# Patch embedding (timm PatchEmbed = Conv2d(k=s=P)) as im2col + GEMM -- run_vit_training.py:124,156
+# ------------------------------------------------------------------------------------------------
+def patch_im2col(images, P: int, kpad: int, dtype):
+    B, C, S, _ = images.shape
+    G = S // P
+    cols = images.view(B, C, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, C * P * P)
+    out = torch.zeros(B * G * G, kpad, dtype=dtype, device=images.device)
+    out[:, : C * P * P] = cols.to(dtype)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Loss (torch.nn.CrossEntropyLoss, mean) -- run_vit_training.py:229,262 ; eval argmax -- :312-313
+# ------------------------------------------------------------------------------------------------
+def cross_entropy(logits, target, want_grad: bool = True):
+    lf = _f32(logits)
+    lse = torch.logsumexp(lf, dim=-1)
+    picked = lf.gather(1, target.view(-1, 1)).squeeze(1)
+    loss = (lse - picked).mean()
+    dlogits = None
+    if want_grad:
+        prob = torch.exp(lf - lse[:, None])
+        prob[torch.arange(lf.shape[0], device=lf.device), target] -= 1.0
+        dlogits = (prob / lf.shape[0]).to(logits.dtype)
+    correct = (lf.argmax(dim=-1) == target).sum()
+    return loss, dlogits, correct
+
+
+# ------------------------------------------------------------------------------------------------
+# Optimizer pieces (torch.optim.AdamW + clip_grad_norm_) -- run_vit_training.py:237,270,278
+# ------------------------------------------------------------------------------------------------
+def sumsq(x, out):
+    out += _f32(x).pow(2).sum()
+
+
+def clip_coef(sumsq_t, max_norm: float):
+    norm = torch.sqrt(sumsq_t)
+    return torch.clamp(max_norm / (norm + 1e-6), max=1.0), norm
+
+
+def adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
+    g = _f32(grad)
+    if clip is not None:
+        g = g * clip
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    w.mul_(1.0 - lr * wd)
+    denom = (v / bc2).sqrt_().add_(eps)
+    w.addcdiv_(m / bc1, denom, value=-lr)
