@@ -1,0 +1,274 @@
+"""Vision Transformer as an explicit functional graph with hand-written forward *and* backward.
+
+Architecture parity with the reference model (run_vit_training.py:99-162, timm 0.4.12 blocks):
+  * PatchEmbed = Conv2d(3, D, k=s=P) -> tokens; learned pos_embed; dropout           (:124-129,156-157)
+  * num_blocks pre-LN blocks: x += proj(attn(norm1(x))); x += fc2(gelu(fc1(norm2(x))))  (:133-141)
+    - LayerNorm eps 1e-5 inside blocks, qkv_bias=True, exact (erf) GELU, no drop-path
+  * final LayerNorm(eps=1e-6), mean-pool over tokens (no CLS token), Linear head      (:151-153,159-161)
+Parameter names are timm-compatible (``norm1.weight``, ``attn.qkv.weight``, ``mlp.fc1.bias`` ...).
+
+There is no autograd here: every stage has an explicit backward, which is what lets the FSDP engine
+place every gather / reduce-scatter / free deterministically and write weight gradients straight into
+the flat per-unit gradient buffer.  ``ops`` is either ``torch_ops`` (reference, CPU) or ``cuda_ops``
+(sm_100a kernels); both expose the same functions.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ..config import ViTConfig
+
+BLOCK_LN_EPS = 1e-5  # timm Block default norm_layer=nn.LayerNorm (eps 1e-5)
+FINAL_LN_EPS = 1e-6  # run_vit_training.py:151
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter inventory
+# ------------------------------------------------------------------------------------------------
+def block_param_specs(cfg: ViTConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    D, Hd = cfg.embed_dim, cfg.hidden_dim
+    return [
+        ("norm1.weight", (D,)), ("norm1.bias", (D,)),
+        ("attn.qkv.weight", (3 * D, D)), ("attn.qkv.bias", (3 * D,)),
+        ("attn.proj.weight", (D, D)), ("attn.proj.bias", (D,)),
+        ("norm2.weight", (D,)), ("norm2.bias", (D,)),
+        ("mlp.fc1.weight", (Hd, D)), ("mlp.fc1.bias", (Hd,)),
+        ("mlp.fc2.weight", (D, Hd)), ("mlp.fc2.bias", (D,)),
+    ]
+
+
+def root_param_specs(cfg: ViTConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Root unit.  The conv weight is stored as a [D, Kpad] GEMM operand (logical [D, 3, P, P])."""
+    D = cfg.embed_dim
+    return [
+        ("patch_embed.proj.weight", (D, cfg.patch_kpad)), ("patch_embed.proj.bias", (D,)),
+        ("pos_embed", (cfg.num_patches, D)),
+        ("norm.weight", (D,)), ("norm.bias", (D,)),
+        ("head.weight", (cfg.num_classes, D)), ("head.bias", (cfg.num_classes,)),
+    ]
+
+
+def logical_shapes(cfg: ViTConfig) -> Dict[str, Tuple[int, ...]]:
+    """Shapes a plain timm-style (non-sharded) ViT would have for the stored tensors that differ."""
+    P = cfg.patch_size
+    return {"patch_embed.proj.weight": (cfg.embed_dim, 3, P, P), "pos_embed": (1, cfg.num_patches, cfg.embed_dim)}
+
+
+def _linear_init(out_f: int, in_f: int, gen, fan_in: Optional[int] = None):
+    """PyTorch's default nn.Linear / nn.Conv2d init (kaiming_uniform a=sqrt(5)): U(+-1/sqrt(fan_in)).
+
+    The reference calls timm's ``_init_vit_weights`` on composite modules where it matches nothing
+    (run_vit_training.py:125,142), so every Linear/Conv keeps this default init.
+    """
+    fan_in = fan_in or in_f
+    bound = 1.0 / math.sqrt(fan_in)
+    w = (torch.rand(out_f, in_f, generator=gen) * 2.0 - 1.0) * bound
+    b = (torch.rand(out_f, generator=gen) * 2.0 - 1.0) * bound
+    return w, b
+
+
+def init_block_params(cfg: ViTConfig, gen) -> Dict[str, torch.Tensor]:
+    D, Hd = cfg.embed_dim, cfg.hidden_dim
+    p = {"norm1.weight": torch.ones(D), "norm1.bias": torch.zeros(D),
+         "norm2.weight": torch.ones(D), "norm2.bias": torch.zeros(D)}
+    p["attn.qkv.weight"], p["attn.qkv.bias"] = _linear_init(3 * D, D, gen)
+    p["attn.proj.weight"], p["attn.proj.bias"] = _linear_init(D, D, gen)
+    p["mlp.fc1.weight"], p["mlp.fc1.bias"] = _linear_init(Hd, D, gen)
+    p["mlp.fc2.weight"], p["mlp.fc2.bias"] = _linear_init(D, Hd, gen)
+    return p
+
+
+def init_root_params(cfg: ViTConfig, gen) -> Dict[str, torch.Tensor]:
+    D = cfg.embed_dim
+    p = {}
+    w, b = _linear_init(D, cfg.patch_k, gen)
+    wp = torch.zeros(D, cfg.patch_kpad)
+    wp[:, : cfg.patch_k] = w
+    p["patch_embed.proj.weight"], p["patch_embed.proj.bias"] = wp, b
+    pos = torch.empty(cfg.num_patches, D)
+    torch.nn.init.trunc_normal_(pos, std=0.02, generator=gen)  # run_vit_training.py:128
+    p["pos_embed"] = pos
+    p["norm.weight"], p["norm.bias"] = torch.ones(D), torch.zeros(D)
+    p["head.weight"], p["head.bias"] = _linear_init(cfg.num_classes, D, gen)
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# Dropout (reference flags --pos_dropout / --att_dropout / --mlp_dropout, default 0 -> elided)
+# ------------------------------------------------------------------------------------------------
+class DropoutCtx:
+    """Counter-based dropout masks: mask(site) is a pure function of (seed, step, site), so the
+    activation-checkpoint recompute regenerates exactly the mask the first forward used."""
+
+    def __init__(self, seed: int = 0):
+        self.seed = seed
+        self.step = 0
+        self.training = True
+
+    def mask(self, shape, p: float, site: int, device):
+        if p <= 0.0 or not self.training:
+            return None
+        gen = torch.Generator(device=device)
+        gen.manual_seed((self.seed * 1000003 + self.step) * 1000003 + site)
+        return torch.rand(shape, generator=gen, device=device) >= p
+
+
+def _apply_mask(t, mask, p):
+    if mask is None:
+        return t
+    return (t.float() * mask * (1.0 / (1.0 - p))).to(t.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Transformer block
+# ------------------------------------------------------------------------------------------------
+def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[DropoutCtx] = None,
+                  block_idx: int = 0):
+    """x: [B*N, D] -> y: [B*N, D].  With save=True also returns the tensors backward needs."""
+    N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
+    pa, pm = cfg.att_dropout, cfg.mlp_dropout
+    use_drop = drop is not None and drop.training and (pa > 0 or pm > 0)
+    site = block_idx * 8
+    h1, m1, r1 = ops.ln_fwd(x, p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)
+    qkv = ops.linear_fwd(h1, p["attn.qkv.weight"], p["attn.qkv.bias"])
+    masks = {}
+    if use_drop and pa > 0:
+        masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
+        a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
+    else:
+        a, P = ops.attention_fwd(qkv, B, N, H, hd)
+    if use_drop and pm > 0:
+        # timm feeds `drop` to both proj_drop and the two MLP dropouts
+        masks["proj"] = drop.mask(x.shape, pm, site + 1, x.device)
+        t = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"])
+        x1 = (x.float() + _apply_mask(t, masks["proj"], pm).float()).to(x.dtype)
+    else:
+        x1 = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"], residual=x)
+    h2, m2, r2 = ops.ln_fwd(x1, p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)
+    if save:
+        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", want_preact=True)
+    else:
+        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu"), None
+    if use_drop and pm > 0:
+        masks["fc1"] = drop.mask(g.shape, pm, site + 2, x.device)
+        masks["fc2"] = drop.mask(x.shape, pm, site + 3, x.device)
+        g = _apply_mask(g, masks["fc1"], pm)
+        t = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"])
+        y = (x1.float() + _apply_mask(t, masks["fc2"], pm).float()).to(x.dtype)
+    else:
+        y = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"], residual=x1)
+    if not save:
+        return y, None
+    saved = dict(x=x, m1=m1, r1=r1, h1=h1, qkv=qkv, P=P, a=a, x1=x1, m2=m2, r2=r2, h2=h2, u=u, g=g, masks=masks)
+    return y, saved
+
+
+def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
+    """Backward of one block.
+
+    p / G: parameter and gradient views of this unit.  dy_colsum = column sums of dy (fp32), which *is*
+    the fc2 bias gradient; it is produced for free by whoever computed dy (the LN backward of the block
+    above).  Returns (dx, colsum(dx)) for the block below.
+    """
+    N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
+    pa, pm = cfg.att_dropout, cfg.mlp_dropout
+    masks = s["masks"]
+    # ---- MLP ----
+    if "fc2" in masks:
+        dt = _apply_mask(dy, masks["fc2"], pm)
+        G["mlp.fc2.bias"].copy_(ops.colsum(dt))
+    else:
+        dt = dy
+        G["mlp.fc2.bias"].copy_(dy_colsum)
+    ops.linear_wgrad(dt, s["g"], out=G["mlp.fc2.weight"])
+    if "fc1" in masks:
+        dg = _apply_mask(ops.linear_dgrad(dt, p["mlp.fc2.weight"]), masks["fc1"], pm)
+        du = (dg.float() * ops_dgelu(ops, s["u"])).to(dy.dtype)
+        db1 = ops.colsum(du)
+    else:
+        du, db1 = ops.linear_dgrad(dt, p["mlp.fc2.weight"], dgelu_preact=s["u"], want_colsum=True)
+    G["mlp.fc1.bias"].copy_(db1)
+    ops.linear_wgrad(du, s["h2"], out=G["mlp.fc1.weight"])
+    dh2 = ops.linear_dgrad(du, p["mlp.fc1.weight"])
+    del du
+    dx1, dn2w, dn2b, dx1_sum = ops.ln_bwd(dh2, s["x1"], p["norm2.weight"], s["m2"], s["r2"], dres=dy, want_dxsum=True)
+    del dh2
+    G["norm2.weight"].copy_(dn2w)
+    G["norm2.bias"].copy_(dn2b)
+    # ---- attention ----
+    if "proj" in masks:
+        dt = _apply_mask(dx1, masks["proj"], pm)
+        G["attn.proj.bias"].copy_(ops.colsum(dt))
+    else:
+        dt = dx1
+        G["attn.proj.bias"].copy_(dx1_sum)
+    ops.linear_wgrad(dt, s["a"], out=G["attn.proj.weight"])
+    da = ops.linear_dgrad(dt, p["attn.proj.weight"])
+    if "att" in masks:
+        dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True, drop_mask=masks["att"],
+                                        drop_scale=1.0 / (1.0 - pa))
+    else:
+        dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True)
+    del da
+    G["attn.qkv.bias"].copy_(dbqkv)
+    ops.linear_wgrad(dqkv, s["h1"], out=G["attn.qkv.weight"])
+    dh1 = ops.linear_dgrad(dqkv, p["attn.qkv.weight"])
+    del dqkv
+    dx, dn1w, dn1b, dx_sum = ops.ln_bwd(dh1, s["x"], p["norm1.weight"], s["m1"], s["r1"], dres=dx1, want_dxsum=True)
+    G["norm1.weight"].copy_(dn1w)
+    G["norm1.bias"].copy_(dn1b)
+    return dx, dx_sum
+
+
+def ops_dgelu(ops, u):
+    from ..ops import torch_ops
+
+    return torch_ops.dgelu(u)
+
+
+# ------------------------------------------------------------------------------------------------
+# Stem (patch embed + pos embed) and head (final norm, mean pool, classifier, loss)
+# ------------------------------------------------------------------------------------------------
+def stem_forward(ops, cfg: ViTConfig, p, images, dtype, drop: Optional[DropoutCtx] = None):
+    B = images.shape[0]
+    cols = ops.patch_im2col(images, cfg.patch_size, cfg.patch_kpad, dtype)
+    x0 = ops.linear_fwd(cols, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], residual=p["pos_embed"],
+                        res_row_mod=cfg.num_patches)
+    mask = None
+    if drop is not None and cfg.pos_dropout > 0:
+        mask = drop.mask(x0.shape, cfg.pos_dropout, 7_000_001, x0.device)
+        x0 = _apply_mask(x0, mask, cfg.pos_dropout)
+    return x0, dict(cols=cols, mask=mask, B=B)
+
+
+def stem_backward(ops, cfg: ViTConfig, p, G, s, dx0, dx0_colsum):
+    if s["mask"] is not None:
+        dx0 = _apply_mask(dx0, s["mask"], cfg.pos_dropout)
+        dx0_colsum = ops.colsum(dx0)
+    ops.linear_wgrad(dx0, s["cols"], out=G["patch_embed.proj.weight"])
+    G["patch_embed.proj.bias"].copy_(dx0_colsum)
+    G["pos_embed"].copy_(dx0.view(s["B"], cfg.num_patches, cfg.embed_dim).sum(dim=0, dtype=torch.float32))
+
+
+def head_forward(ops, cfg: ViTConfig, p, x, B: int):
+    """logits = head(mean_tokens(norm(x)))   (run_vit_training.py:161)"""
+    N, D = cfg.num_patches, cfg.embed_dim
+    xn, m, r = ops.ln_fwd(x, p["norm.weight"], p["norm.bias"], FINAL_LN_EPS)
+    pooled = xn.view(B, N, D).mean(dim=1, dtype=torch.float32).to(x.dtype)
+    logits = ops.linear_fwd(pooled, p["head.weight"], p["head.bias"])
+    return logits, dict(x=x, m=m, r=r, pooled=pooled)
+
+
+def head_backward(ops, cfg: ViTConfig, p, G, s, dlogits, B: int):
+    N, D = cfg.num_patches, cfg.embed_dim
+    ops.linear_wgrad(dlogits, s["pooled"], out=G["head.weight"])
+    G["head.bias"].copy_(dlogits.sum(dim=0, dtype=torch.float32))
+    dpooled = ops.linear_dgrad(dlogits, p["head.weight"])
+    dxn = (dpooled.float() / N).to(dpooled.dtype)[:, None, :].expand(B, N, D).reshape(B * N, D)
+    dx, dnw, dnb, dx_sum = ops.ln_bwd(dxn, s["x"], p["norm.weight"], s["m"], s["r"], want_dxsum=True)
+    G["norm.weight"].copy_(dnw)
+    G["norm.bias"].copy_(dnb)
+    return dx, dx_sum

@@ -196,3 +196,24 @@ def adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
     w.mul_(1.0 - lr * wd)
     denom = (v / bc2).sqrt_().add_(eps)
     w.addcdiv_(m / bc1, denom, value=-lr)
+
+
+# Split fp32 master representation: fp32 bits == (hi_bf16_bits << 16) + lo_int16, hi = RN-even bf16.
+def split_fp32(w, hi, lo):
+    bits = w.contiguous().view(torch.int32)
+    rounded = bits + 0x7FFF + ((bits >> 16) & 1)
+    h = rounded >> 16
+    hi.copy_((h << 16).view(torch.float32).to(torch.bfloat16))
+    lo.copy_((bits - (h << 16)).to(torch.int16))
+
+
+def merge_fp32(hi, lo, w):
+    bits = (hi.view(torch.int16).to(torch.int32) << 16) + lo.to(torch.int32)
+    w.copy_(bits.view(torch.float32))
+
+
+def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
+    w = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
+    merge_fp32(hi, lo, w)
+    adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)
+    split_fp32(w, hi, lo)

@@ -1,0 +1,3 @@
+from .engine import FSDPViT, FsdpUnit  # noqa: F401
+from .layout import UnitLayout  # noqa: F401
+from .optim import ShardedAdamW  # noqa: F401

@@ -1,0 +1,228 @@
+"""Collective backends of the FSDP engine.
+
+``TorchDistBackend``  torch.distributed collectives (gloo on CPU, NCCL on GPU).  It is the CPU test vehicle
+                      and the honest NCCL baseline -- *not* the product path on B200.
+``Sm100Backend``      hand-written NVLink 5 / NVSwitch kernels over symmetric memory (csrc/comm.cu):
+                      sync-free peer-to-peer all-gather that lands shards in their final position,
+                      one-pass reduce-scatter (+1/W mean, +fp32 cast, +grad-norm partial) with optional
+                      in-switch NVLS reduction, flag barriers and scalar all-reduce.  No NCCL on the hot path.
+
+Both implement the same small interface used by ``engine.FSDPViT``:
+    alloc_shard / alloc_full_grad / all_gather / reduce_scatter / all_reduce_scalars_ / all_reduce_mean_ / barrier
+(replaces torch_xla's XLA collectives + xm.mesh_reduce / xm.rendezvous, reference run_vit_training.py:177-181,
+205,224,270,273).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .layout import UnitLayout
+
+
+class TorchDistBackend:
+    name = "torchdist"
+
+    def __init__(self, world: int, rank: int, device: torch.device):
+        self.world, self.rank, self.device = world, rank, device
+        self.is_gloo = world > 1 and dist.get_backend() == "gloo"
+
+    # ---- allocation (plain device memory) ----
+    def alloc_shard(self, numel: int, dtype) -> torch.Tensor:
+        return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    def alloc_full_grad(self, numel: int, dtype) -> torch.Tensor:
+        return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    # ---- collectives ----
+    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor) -> None:
+        if self.world == 1:
+            if out_full.data_ptr() != shard.data_ptr():
+                out_full[: shard.numel()].copy_(shard)
+            return
+        if len(layout.groups) == 1:  # flat parameter: the gathered tensor *is* the full buffer
+            dist.all_gather_into_tensor(out_full[: layout.full_numel], shard)
+            return
+        staging = torch.empty(self.world * layout.shard_numel, dtype=shard.dtype, device=shard.device)
+        dist.all_gather_into_tensor(staging, shard)
+        st = staging.view(self.world, layout.shard_numel)
+        for g in layout.groups:  # copy-out (this pass is what the P2P kernel avoids)
+            out_full[g.full_offset: g.full_offset + self.world * g.shard_len].view(self.world, g.shard_len).copy_(
+                st[:, g.shard_offset: g.shard_offset + g.shard_len])
+
+    def reduce_scatter(self, layout: UnitLayout, full_grad: torch.Tensor, out_shard: torch.Tensor,
+                       sumsq: Optional[torch.Tensor] = None, ops=None) -> None:
+        """out_shard (fp32) = mean over ranks of this rank's slices of full_grad; sumsq += |out_shard|^2."""
+        W = self.world
+        if W == 1:
+            if out_shard.data_ptr() != full_grad.data_ptr():
+                out_shard.copy_(full_grad[: out_shard.numel()])
+        else:
+            staging = torch.empty(W, layout.shard_numel, dtype=torch.float32, device=full_grad.device)
+            for g in layout.groups:  # copy-in, fp32 so the reduction accumulates in fp32
+                staging[:, g.shard_offset: g.shard_offset + g.shard_len].copy_(
+                    full_grad[g.full_offset: g.full_offset + W * g.shard_len].view(W, g.shard_len))
+            if self.is_gloo:
+                dist.all_reduce(staging)
+                out_shard.copy_(staging[self.rank])
+            else:
+                dist.reduce_scatter_tensor(out_shard, staging.view(-1))
+            out_shard.mul_(1.0 / W)
+        if sumsq is not None:
+            ops.sumsq(out_shard, sumsq)
+
+    def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+        return t
+
+    def all_reduce_mean_(self, t: torch.Tensor) -> torch.Tensor:
+        """DDP-style gradient all-reduce (reference --run_without_fsdp, xm.reduce_gradients :273)."""
+        if self.world > 1:
+            if t.dtype == torch.bfloat16 and self.is_gloo:
+                f = t.float()
+                dist.all_reduce(f)
+                t.copy_(f.mul_(1.0 / self.world))
+            else:
+                dist.all_reduce(t)
+                t.mul_(1.0 / self.world)
+        return t
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            dist.barrier()
+
+    def step_begin(self) -> None:
+        pass
+
+    def params_updated(self) -> None:
+        pass
+
+
+class Sm100Backend(TorchDistBackend):
+    """Symmetric-memory NVLink backend.  Falls back to the parent (NCCL) only for host-side utilities."""
+
+    name = "sm100"
+    FLAG_BYTES = 64 * 1024  # flags: uint32[slot][16]; scratch floats follow at +32 KiB
+
+    def __init__(self, world: int, rank: int, device: torch.device, comm_ctas: int = 24):
+        super().__init__(world, rank, device)
+        from ..ops import native
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._C = native.load()
+        self._symm = symm_mem
+        self.comm_ctas = comm_ctas
+        self._handles = []   # keep rendezvous handles alive
+        self._peer = {}      # data_ptr of a symmetric tensor -> list of peer base pointers
+        self._mc = {}        # data_ptr -> multicast base pointer (0 if unsupported)
+        self._seg_cache = {}
+        self._seq = {}       # slot -> sequence number
+        self.group_name = dist.group.WORLD.group_name
+        ctrl = self._symm_alloc(self.FLAG_BYTES, torch.uint8)
+        ctrl.zero_()
+        self._ctrl = ctrl
+        self._flag_ptrs = self._peer[ctrl.data_ptr()]
+        self._scratch_ptrs = [p + 32 * 1024 for p in self._flag_ptrs]
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.use_nvls = all(v != 0 for v in self._mc.values())
+
+    # ---- symmetric allocation ----
+    def _symm_alloc(self, numel: int, dtype) -> torch.Tensor:
+        t = self._symm.empty(numel, dtype=dtype, device=self.device)
+        hdl = self._symm.rendezvous(t, dist.group.WORLD)
+        self._handles.append((t, hdl))
+        self._peer[t.data_ptr()] = [int(p) for p in hdl.buffer_ptrs]
+        mc = 0
+        try:
+            if hdl.has_multicast_support:
+                mc = int(hdl.multicast_ptr)
+        except Exception:
+            mc = 0
+        self._mc[t.data_ptr()] = mc
+        return t
+
+    def alloc_shard(self, numel: int, dtype) -> torch.Tensor:
+        t = self._symm_alloc(numel, dtype)
+        t.zero_()
+        return t
+
+    def alloc_full_grad(self, numel: int, dtype) -> torch.Tensor:
+        t = self._symm_alloc(numel, dtype)
+        t.zero_()
+        return t
+
+    def _next_seq(self, slot: int) -> int:
+        self._seq[slot] = self._seq.get(slot, 0) + 1
+        return self._seq[slot]
+
+    def device_barrier(self, slot: int = 0) -> None:
+        """Stream-ordered cross-GPU barrier on the current stream (flags in symmetric memory)."""
+        self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, self._next_seq(slot))
+
+    # ---- segment tables (device int64), built once per (layout, purpose) ----
+    def _ag_table(self, layout: UnitLayout, esize: int):
+        key = ("ag", id(layout), esize)
+        if key not in self._seg_cache:
+            chunk = self._C.ag_chunk_bytes()
+            rows, prefix = [], 0
+            for (r, soff, doff, n) in layout.gather_segments():
+                rows.append([r, soff * esize, doff * esize, n * esize, prefix])
+                prefix += -(-n * esize // chunk)
+            self._seg_cache[key] = (torch.tensor(rows, dtype=torch.int64, device=self.device), prefix)
+        return self._seg_cache[key]
+
+    def _rs_table(self, layout: UnitLayout, esize: int):
+        key = ("rs", id(layout), esize)
+        if key not in self._seg_cache:
+            chunk = self._C.rs_chunk_elems()
+            rows, prefix = [], 0
+            for (foff, soff, n) in layout.scatter_segments(self.rank):
+                rows.append([foff * esize, soff, n, prefix])
+                prefix += -(-n // chunk)
+            self._seg_cache[key] = (torch.tensor(rows, dtype=torch.int64, device=self.device), prefix)
+        return self._seg_cache[key]
+
+    # ---- collectives ----
+    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor) -> None:
+        if self.world == 1:
+            return super().all_gather(layout, shard, out_full)
+        table, chunks = self._ag_table(layout, shard.element_size())
+        self._C.p2p_all_gather(self._peer[shard.data_ptr()], self.rank, out_full, table, chunks, self.comm_ctas)
+
+    def reduce_scatter(self, layout: UnitLayout, full_grad: torch.Tensor, out_shard: torch.Tensor,
+                       sumsq: Optional[torch.Tensor] = None, ops=None) -> None:
+        if self.world == 1:
+            return super().reduce_scatter(layout, full_grad, out_shard, sumsq, ops)
+        table, chunks = self._rs_table(layout, full_grad.element_size())
+        scale = 1.0 / self.world
+        self.device_barrier(slot=1)  # every rank's gradients for this unit are complete
+        if self.use_nvls and full_grad.dtype == torch.bfloat16:
+            self._C.nvls_reduce_scatter(self._mc[full_grad.data_ptr()], self.rank, self.world, out_shard, table,
+                                        chunks, scale, sumsq, self.comm_ctas)
+        else:
+            self._C.p2p_reduce_scatter(self._peer[full_grad.data_ptr()], self.rank, out_shard, table, chunks,
+                                       full_grad.dtype == torch.bfloat16, scale, sumsq, self.comm_ctas)
+        self.device_barrier(slot=2)  # every rank is done reading: the buffer may be overwritten
+
+    def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        if self.world > 1:
+            assert t.dtype == torch.float32 and t.numel() <= 16
+            seq = self._next_seq(3)
+            self._C.allreduce_scalars(self._flag_ptrs, self._scratch_ptrs, self.rank, self.world, 4 + (seq & 1), seq,
+                                      t, 0 if op == "sum" else 1)
+        return t
+
+    def params_updated(self) -> None:
+        """Shards were rewritten by the optimizer: peers may only pull them after everyone is done."""
+        if self.world > 1:
+            self.device_barrier(slot=0)
+
+
+def make_backend(kind: str, world: int, rank: int, device: torch.device):
+    if kind == "sm100":
+        return Sm100Backend(world, rank, device)
+    return TorchDistBackend(world, rank, device)

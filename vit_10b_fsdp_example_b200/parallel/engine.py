@@ -1,0 +1,454 @@
+"""Hand-rolled fully-sharded data-parallel (ZeRO-3 / ZeRO-2 / DDP) engine for the functional ViT.
+
+What the reference gets from ``XlaFullyShardedDataParallel`` + ``checkpoint_module`` + XLA's scheduler
+(run_vit_training.py:165-200, 261-280) is implemented here explicitly:
+
+  * one FSDP unit per transformer block + one root unit (patch/pos embed, final norm, head)   (:145,199)
+  * each rank keeps only its shard of every unit's parameters, gradients and AdamW state      (:177-181,237)
+  * forward : all-gather unit i+1 (comm stream) while unit i computes; free after use when
+              ``reshard_after_forward`` (ZeRO-3) or keep until backward (ZeRO-2-like)            (:174,358)
+  * backward: re-gather, recompute the block from its checkpointed input (``grad_ckpt``), run the
+              hand-written backward, reduce-scatter (mean) the unit's gradients while the next block
+              computes -> 2 all-gathers + 1 reduce-scatter per block per step                    (:194,357)
+  * ``clip_grad_norm_`` over the *full* gradient (local sum of squares -> all-reduce)           (:266-270)
+  * ``--run_without_fsdp``: replicated parameters + gradient all-reduce (DDP comparison mode)   (:171-172,271-275)
+  * ``--shard_on_cpu``: blocks are built, sharded on the host one at a time, only shards reach HBM (:175-178)
+  * sharded ``state_dict`` / ``load_state_dict`` / ``get_shard_metadata``                       (utils.py:26-40)
+
+Memory layout (bf16 compute): the fp32 master weight of a shard is stored *split* as (bf16 hi, int16 lo);
+``hi`` is simultaneously the tensor peers all-gather from, so there is no separate low-precision copy and
+no cast pass.  On one GPU the gathered buffer aliases the shard itself (zero-copy).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional
+
+import torch
+
+from ..config import ViTConfig
+from ..models import vit
+from .backends import make_backend
+from .layout import UnitLayout
+
+
+class _NullEvent:
+    def record(self, *a, **k):
+        pass
+
+    def wait(self, *a, **k):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class FsdpUnit:
+    """Sharded state of one FSDP unit on this rank."""
+
+    def __init__(self, name: str, layout: UnitLayout, index: int):
+        self.name, self.layout, self.index = name, layout, index
+        self.master: Optional[torch.Tensor] = None   # fp32 shard (fp32 compute mode)
+        self.hi: Optional[torch.Tensor] = None       # bf16 shard  (bf16 compute mode; also the all-gather source)
+        self.lo: Optional[torch.Tensor] = None       # int16 remainder so (hi<<16)+lo == fp32 master bits
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.shard_grad: Optional[torch.Tensor] = None
+        self.full: Optional[torch.Tensor] = None     # gathered parameters (compute dtype) while resident
+        self.full_grad: Optional[torch.Tensor] = None
+        self.gather_event = None
+        self.reduce_event = None
+
+    @property
+    def compute_shard(self) -> torch.Tensor:
+        return self.hi if self.hi is not None else self.master
+
+
+class FSDPViT:
+    """The sharded model: ``loss = model.forward_backward(images, target)``; ``logits = model(images)``."""
+
+    def __init__(self, vcfg: ViTConfig, *, world: int = 1, rank: int = 0, device=None, dtype=torch.float32,
+                 reshard_after_forward: bool = True, flatten_parameters: bool = False, grad_ckpt: bool = True,
+                 run_without_fsdp: bool = False, shard_on_cpu: bool = False, backend: str = "torchdist",
+                 seed: int = 0, init_device: str = "cpu", verbose_build=None):
+        self.cfg = vcfg
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.dtype = dtype
+        self.dp_world, self.rank = world, rank
+        self.use_fsdp = not run_without_fsdp
+        # In DDP comparison mode every rank holds everything: shard math runs with world = 1.
+        self.world = world if self.use_fsdp else 1
+        self.shard_rank = rank if self.use_fsdp else 0
+        self.reshard_after_forward = reshard_after_forward
+        self.flatten_parameters = flatten_parameters
+        self.grad_ckpt = grad_ckpt
+        self.shard_on_cpu = shard_on_cpu
+        self.training = True
+        self.is_cuda = self.device.type == "cuda"
+        self.split_master = dtype == torch.bfloat16
+        if self.is_cuda:
+            from ..ops import cuda_ops
+
+            assert dtype == torch.bfloat16, "the sm_100a kernel path is bf16 (use --device cpu for fp32 reference runs)"
+            self.ops = cuda_ops
+        else:
+            from ..ops import torch_ops
+
+            self.ops = torch_ops
+        self.backend = make_backend(backend if self.is_cuda else "torchdist", world, rank, self.device)
+        self.drop = vit.DropoutCtx(seed)
+        self._clip_coef = None
+        self._grad_norm = None
+        self._sumsq = None
+        self._fused_sumsq = False
+        self.step_count = 0
+
+        # ---- streams ----
+        if self.is_cuda:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        else:
+            self.comm_stream = None
+
+        # ---- units: blocks are built / sharded ONE AT A TIME (host peak = one full block) ----
+        self.units: List[FsdpUnit] = []
+        bspecs, rspecs = vit.block_param_specs(vcfg), vit.root_param_specs(vcfg)
+        gen_device = "cpu" if (shard_on_cpu or init_device == "cpu" or not self.is_cuda) else self.device
+        for i in range(vcfg.num_blocks):
+            lay = UnitLayout.build(f"blocks.{i}", bspecs, self.world, flatten_parameters)
+            unit = FsdpUnit(lay.name, lay, i)
+            self._init_unit(unit, lambda g: vit.init_block_params(vcfg, g), seed * 100003 + i + 1, gen_device)
+            self.units.append(unit)
+            if verbose_build is not None:
+                verbose_build(f"built ViT block {i}")  # run_vit_training.py:147
+        lay = UnitLayout.build("root", rspecs, self.world, flatten_parameters)
+        self.root = FsdpUnit("root", lay, vcfg.num_blocks)
+        self._init_unit(self.root, lambda g: vit.init_root_params(vcfg, g), seed * 100003, gen_device)
+        self.blocks = self.units
+        self.all_units = self.units + [self.root]
+
+        # ---- transient buffers ----
+        self._setup_buffers()
+        self.backend.params_updated()
+
+    # ------------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------------
+    def _init_unit(self, unit: FsdpUnit, init_fn, seed: int, gen_device) -> None:
+        lay = unit.layout
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        params = init_fn(gen)  # fp32, host
+        work_dev = "cpu" if (self.shard_on_cpu or not self.is_cuda) else self.device
+        full = torch.zeros(lay.full_numel, dtype=torch.float32, device=work_dev)
+        for p in lay.params:
+            full[p.full_offset: p.full_offset + p.numel].copy_(params[p.name].reshape(-1))
+        del params
+        shard = torch.zeros(lay.shard_numel, dtype=torch.float32, device=work_dev)
+        lay.shard_from_full(full, self.shard_rank, shard)
+        del full
+        self._install_master(unit, shard.to(self.device))
+        n = lay.shard_numel
+        unit.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        unit.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+
+    def _install_master(self, unit: FsdpUnit, shard_fp32: torch.Tensor) -> None:
+        n = unit.layout.shard_numel
+        if self.split_master:
+            if unit.hi is None:
+                unit.hi = self.backend.alloc_shard(n, torch.bfloat16)
+                unit.lo = torch.empty(n, dtype=torch.int16, device=self.device)
+            self.ops.split_fp32(shard_fp32, unit.hi, unit.lo)
+        else:
+            if unit.master is None:
+                unit.master = self.backend.alloc_shard(n, torch.float32)
+            unit.master.copy_(shard_fp32)
+
+    def master_fp32(self, unit: FsdpUnit) -> torch.Tensor:
+        """This rank's fp32 master shard (reconstructed exactly from the split representation)."""
+        if not self.split_master:
+            return unit.master
+        out = torch.empty(unit.layout.shard_numel, dtype=torch.float32, device=self.device)
+        self.ops.merge_fp32(unit.hi, unit.lo, out)
+        return out
+
+    def _setup_buffers(self) -> None:
+        W = self.world
+        blocks = self.units
+        max_full = max(u.layout.full_numel for u in blocks) if blocks else 0
+        self._alias = W == 1  # gathered buffer == shard buffer, gradient buffer == shard gradient
+        self._free_events: Dict[int, object] = {}
+        if self._alias:
+            for u in self.all_units:
+                u.full = u.compute_shard
+                u.full_grad = self.backend.alloc_full_grad(u.layout.full_numel, self.dtype)
+                u.shard_grad = u.full_grad
+            self._param_bufs, self._grad_bufs = [], []
+            return
+        n_param_bufs = 2 if self.reshard_after_forward else len(blocks)
+        self._param_bufs = [torch.empty(max_full, dtype=self.dtype, device=self.device) for _ in range(n_param_bufs)]
+        self._grad_bufs = [self.backend.alloc_full_grad(max_full, self.dtype) for _ in range(min(2, max(1, len(blocks))))]
+        self._param_buf_free = [self._new_event() for _ in self._param_bufs]
+        self._grad_buf_free = [self._new_event() for _ in self._grad_bufs]
+        self.root.full = torch.empty(self.root.layout.full_numel, dtype=self.dtype, device=self.device)
+        self.root.full_grad = self.backend.alloc_full_grad(self.root.layout.full_numel, self.dtype)
+        for u in self.all_units:
+            u.shard_grad = torch.zeros(u.layout.shard_numel, dtype=torch.float32, device=self.device)
+        self._fused_sumsq = self.backend.name == "sm100"
+
+    # ------------------------------------------------------------------------------------------------
+    # stream helpers (no-ops on CPU)
+    # ------------------------------------------------------------------------------------------------
+    def _new_event(self):
+        return torch.cuda.Event() if self.is_cuda else _NullEvent()
+
+    def _on_comm(self):
+        return torch.cuda.stream(self.comm_stream) if self.is_cuda else contextlib.nullcontext()
+
+    def _record(self, ev):
+        if self.is_cuda:
+            ev.record(torch.cuda.current_stream())
+        return ev
+
+    def _wait(self, ev):
+        if self.is_cuda and ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    # ------------------------------------------------------------------------------------------------
+    # gather / reduce scheduling
+    # ------------------------------------------------------------------------------------------------
+    def _param_buf_index(self, unit: FsdpUnit) -> int:
+        return unit.index % len(self._param_bufs)
+
+    def _issue_gather(self, unit: FsdpUnit) -> None:
+        """Enqueue the unit's all-gather on the comm stream (prefetch).  No-op if already resident."""
+        if self._alias or unit.gather_event is not None:
+            return
+        if unit is self.root:
+            buf = unit.full
+            free_ev = None
+        else:
+            bi = self._param_buf_index(unit)
+            buf = self._param_bufs[bi][: unit.layout.full_numel]
+            free_ev = self._param_buf_free[bi]
+        with self._on_comm():
+            self._wait(free_ev)
+            self.backend.all_gather(unit.layout, unit.compute_shard, buf)
+            unit.gather_event = self._record(self._new_event())
+        unit.full = buf
+
+    def _wait_gather(self, unit: FsdpUnit) -> None:
+        if not self._alias:
+            self._wait(unit.gather_event)
+
+    def _release_params(self, unit: FsdpUnit) -> None:
+        """Compute is done with the gathered parameters of this unit (reshard)."""
+        if self._alias or unit is self.root:
+            return
+        self._record(self._param_buf_free[self._param_buf_index(unit)])
+        unit.full = None
+        unit.gather_event = None
+
+    def _grad_views(self, unit: FsdpUnit):
+        if self._alias or unit is self.root:
+            buf = unit.full_grad
+        else:
+            gi = unit.index % len(self._grad_bufs)
+            self._wait(self._grad_buf_free[gi])  # the reduce-scatter that last read this buffer is done
+            buf = self._grad_bufs[gi][: unit.layout.full_numel]
+            unit.full_grad = buf
+        return unit.layout.param_views(buf)
+
+    def _issue_reduce(self, unit: FsdpUnit) -> None:
+        """Gradients of `unit` are complete on the compute stream: reduce-scatter them on the comm stream."""
+        if not self.use_fsdp:
+            ready = self._record(self._new_event())
+            with self._on_comm():
+                self._wait(ready)
+                self.backend.all_reduce_mean_(unit.full_grad[: unit.layout.full_numel])
+                unit.reduce_event = self._record(self._new_event())
+            return
+        if self._alias:
+            return
+        ready = self._record(self._new_event())
+        with self._on_comm():
+            self._wait(ready)
+            self.backend.reduce_scatter(unit.layout, unit.full_grad, unit.shard_grad,
+                                        self._sumsq if self._fused_sumsq else None, self.ops)
+            ev = self._record(self._new_event())
+        unit.reduce_event = ev
+        if unit is not self.root:
+            self._grad_buf_free[unit.index % len(self._grad_bufs)] = ev
+
+    # ------------------------------------------------------------------------------------------------
+    # training step: forward + backward
+    # ------------------------------------------------------------------------------------------------
+    def train(self):
+        self.training = True
+        self.drop.training = True
+        return self
+
+    def eval(self):
+        self.training = False
+        self.drop.training = False
+        return self
+
+    def forward_backward(self, images: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """One micro-step: loss, and this rank's (mean-reduced) shard gradients in ``unit.shard_grad``."""
+        cfg, ops = self.cfg, self.ops
+        B = images.shape[0]
+        blocks = self.units
+        self.drop.step = self.step_count
+        if self._fused_sumsq:
+            self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # -------- forward --------
+        self._issue_gather(self.root)
+        if blocks:
+            self._issue_gather(blocks[0])
+        self._wait_gather(self.root)
+        rp = self.root.layout.param_views(self.root.full)
+        x, stem_saved = vit.stem_forward(ops, cfg, rp, images, self.dtype, self.drop)
+        ckpt: List[torch.Tensor] = []
+        saved_all = []
+        for i, u in enumerate(blocks):
+            if i + 1 < len(blocks):
+                self._issue_gather(blocks[i + 1])
+            self._wait_gather(u)
+            p = u.layout.param_views(u.full)
+            if self.grad_ckpt:
+                ckpt.append(x)
+                x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
+            else:
+                x, s = vit.block_forward(ops, cfg, p, x, B, save=True, drop=self.drop, block_idx=i)
+                saved_all.append(s)
+            if self.reshard_after_forward and i != len(blocks) - 1:
+                self._release_params(u)  # the last block is needed again immediately by backward
+        logits, head_saved = vit.head_forward(ops, cfg, rp, x, B)
+        loss, dlogits, _ = ops.cross_entropy(logits, target, want_grad=True)
+        # -------- backward --------
+        rg = self._grad_views(self.root)
+        dx, dx_sum = vit.head_backward(ops, cfg, rp, rg, head_saved, dlogits, B)
+        del head_saved, logits, dlogits
+        for i in range(len(blocks) - 1, -1, -1):
+            u = blocks[i]
+            self._issue_gather(u)
+            if i - 1 >= 0:
+                self._issue_gather(blocks[i - 1])  # prefetch the next block of the backward sweep
+            self._wait_gather(u)
+            p = u.layout.param_views(u.full)
+            if self.grad_ckpt:
+                xin = ckpt.pop()
+                _, s = vit.block_forward(ops, cfg, p, xin, B, save=True, drop=self.drop, block_idx=i)
+            else:
+                s = saved_all.pop()
+            g = self._grad_views(u)
+            dx, dx_sum = vit.block_backward(ops, cfg, p, g, s, dx, dx_sum, B)
+            del s
+            self._release_params(u)
+            self._issue_reduce(u)
+        vit.stem_backward(ops, cfg, rp, rg, stem_saved, dx, dx_sum)
+        self._issue_reduce(self.root)
+        self.root.gather_event = None  # parameters change in the optimizer step: re-gather next step
+        # compute stream must not run ahead of the reductions it depends on (optimizer / clip read them)
+        for u in self.all_units:
+            self._wait(u.reduce_event)
+            u.reduce_event = None
+        self.step_count += 1
+        return loss
+
+    # ------------------------------------------------------------------------------------------------
+    # inference
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        cfg, ops = self.cfg, self.ops
+        B = images.shape[0]
+        blocks = self.units
+        self._issue_gather(self.root)
+        if blocks:
+            self._issue_gather(blocks[0])
+        self._wait_gather(self.root)
+        rp = self.root.layout.param_views(self.root.full)
+        drop = self.drop if self.training else None
+        x, _ = vit.stem_forward(ops, cfg, rp, images, self.dtype, drop)
+        for i, u in enumerate(blocks):
+            if i + 1 < len(blocks):
+                self._issue_gather(blocks[i + 1])
+            self._wait_gather(u)
+            x, _ = vit.block_forward(ops, cfg, u.layout.param_views(u.full), x, B, save=False, drop=drop, block_idx=i)
+            self._release_params(u)
+        logits, _ = vit.head_forward(ops, cfg, rp, x, B)
+        self.root.gather_event = None
+        return logits
+
+    # ------------------------------------------------------------------------------------------------
+    # gradient clipping (norm of the FULL gradient) -- reference :266-270
+    # ------------------------------------------------------------------------------------------------
+    def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
+        """Computes the global gradient norm and arms the clip coefficient consumed by the next
+        ``optimizer.step()`` (the scaling is fused into the AdamW kernel instead of a separate pass)."""
+        ops = self.ops
+        if self._fused_sumsq and self._sumsq is not None:
+            total = self._sumsq
+        else:
+            total = torch.zeros(1, dtype=torch.float32, device=self.device)
+            for u in self.all_units:
+                ops.sumsq(u.shard_grad, total)
+        if self.use_fsdp:
+            self.backend.all_reduce_scalars_(total, "sum")
+        coef, norm = ops.clip_coef(total, float(max_norm))
+        self._clip_coef, self._grad_norm = coef, norm
+        return norm
+
+    # ------------------------------------------------------------------------------------------------
+    # parameters / state
+    # ------------------------------------------------------------------------------------------------
+    def parameters(self) -> List[torch.Tensor]:
+        """The tensors this rank owns (shards only, like FSDP's ``model.parameters()``; reference :233)."""
+        return [u.compute_shard for u in self.all_units]
+
+    def num_sharded_parameters(self) -> int:
+        return sum(u.layout.shard_numel for u in self.all_units)
+
+    def num_parameters(self) -> int:
+        return sum(u.layout.payload_numel() for u in self.all_units)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Only this rank's shards (fp32, on host), keyed ``<unit>.<param>`` or ``<unit>.flat_param``."""
+        out = {}
+        for u in self.all_units:
+            m = self.master_fp32(u).detach().cpu()
+            for g in u.layout.groups:
+                out[f"{u.name}.{g.name}"] = m[g.shard_offset: g.shard_offset + g.shard_len].clone()
+        return out
+
+    def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+        for u in self.all_units:
+            m = torch.empty(u.layout.shard_numel, dtype=torch.float32)
+            for g in u.layout.groups:
+                t = state[f"{u.name}.{g.name}"]
+                assert t.numel() == g.shard_len, f"shard size mismatch for {u.name}.{g.name} (world size changed?)"
+                m[g.shard_offset: g.shard_offset + g.shard_len].copy_(t)
+            self._install_master(u, m.to(self.device))
+        self.backend.params_updated()
+
+    def get_shard_metadata(self) -> dict:
+        """Everything the offline consolidation tool needs to rebuild full tensors (reference utils.py:29)."""
+        return {
+            "world_size": self.world, "rank": self.shard_rank, "flatten_parameters": self.flatten_parameters,
+            "fsdp": self.use_fsdp, "units": [u.layout.metadata() for u in self.all_units],
+            "logical_shapes": {k: list(v) for k, v in vit.logical_shapes(self.cfg).items()},
+            "patch_k": self.cfg.patch_k,
+            "model": {k: getattr(self.cfg, k) for k in ("image_size", "patch_size", "embed_dim", "num_heads",
+                                                        "num_blocks", "mlp_ratio", "num_classes")},
+        }
+
+    def __repr__(self) -> str:
+        c = self.cfg
+        mode = "FSDP(ZeRO-3)" if self.use_fsdp and self.reshard_after_forward else (
+            "FSDP(ZeRO-2)" if self.use_fsdp else "DDP")
+        return (f"FSDPViT[{mode}, world={self.dp_world}, backend={self.backend.name}, ops={self.ops.NAME}, "
+                f"dtype={self.dtype}]("
+                f"image={c.image_size}, patch={c.patch_size}, dim={c.embed_dim}, heads={c.num_heads}, "
+                f"blocks={c.num_blocks}, mlp_ratio={c.mlp_ratio}, classes={c.num_classes}, "
+                f"grad_ckpt={self.grad_ckpt}, flatten={self.flatten_parameters}, "
+                f"params={self.num_parameters():,}, sharded={self.num_sharded_parameters():,})")

