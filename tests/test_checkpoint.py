@@ -1,0 +1,55 @@
+"""Checkpoint contract: per-rank files, four top-level keys, save->resume == uninterrupted run,
+and offline consolidation reproduces the unsharded parameters bit-exactly."""
+import os
+
+import torch
+
+from dist_worker import launch
+from helpers import full_params_of, tiny_cfg
+from vit_10b_fsdp_example_b200.consolidate_sharded_ckpts import consolidate_files
+from vit_10b_fsdp_example_b200.parallel import FSDPViT
+
+
+def test_resume_equals_uninterrupted(tmp_path):
+    d = str(tmp_path)
+    full = launch(2, {"steps": 5}, os.path.join(d, "full.json"))
+    part = launch(2, {"steps": 3, "save_at": 3, "save_path": os.path.join(d, "epoch_1_rank_{rank}.ckpt")},
+                  os.path.join(d, "part.json"))
+    assert part["losses"] == full["losses"][:3]
+    for r in range(2):
+        ck = torch.load(os.path.join(d, f"epoch_1_rank_{r}.ckpt"), map_location="cpu", weights_only=False)
+        assert sorted(ck.keys()) == ["lr_scheduler", "model", "optimizer", "shard_metadata"]
+        assert ck["shard_metadata"]["rank"] == r and ck["shard_metadata"]["world_size"] == 2
+    rest = launch(2, {"steps": 5, "resume_from": os.path.join(d, "epoch_1_rank_{rank}.ckpt"), "resume_step": 3},
+                  os.path.join(d, "rest.json"))
+    for a, b in zip(rest["losses"], full["losses"][3:]):
+        assert abs(a - b) < 1e-6
+
+
+def test_no_fsdp_checkpoint_has_no_shard_metadata(tmp_path):
+    d = str(tmp_path)
+    launch(1, {"steps": 1, "no_fsdp": True, "save_at": 1, "save_path": os.path.join(d, "epoch_1_rank_{rank}.ckpt")},
+           os.path.join(d, "r.json"))
+    ck = torch.load(os.path.join(d, "epoch_1_rank_0.ckpt"), map_location="cpu", weights_only=False)
+    assert ck["shard_metadata"] is None
+
+
+def test_consolidation_matches_unsharded(tmp_path):
+    d = str(tmp_path)
+    for flatten in (False, True):
+        prefix = os.path.join(d, f"f{int(flatten)}_epoch_1")
+        launch(4, {"steps": 0, "flatten": flatten, "seed": 5, "dump_state": prefix + "_rank_{rank}.ckpt"},
+               os.path.join(d, "r.json"))
+        full = consolidate_files(prefix, save_path=prefix + "_full.pth")
+        cfg = tiny_cfg()
+        ref = full_params_of(FSDPViT(cfg, dtype=torch.float32, seed=5))
+        P = cfg.patch_size
+        assert full["pos_embed"].shape == (1, cfg.num_patches, cfg.embed_dim)
+        assert full["patch_embed.proj.weight"].shape == (cfg.embed_dim, 3, P, P)
+        for k, v in ref.items():
+            got = full[k]
+            if k == "patch_embed.proj.weight":
+                v = v[:, : cfg.patch_k]
+            assert torch.equal(got.reshape(-1), v.reshape(-1)), k
+        saved = torch.load(prefix + "_full.pth", weights_only=False)
+        assert set(saved["model"].keys()) == set(full.keys())

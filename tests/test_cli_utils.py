@@ -1,0 +1,81 @@
+"""CLI compatibility, LR schedule, meters, fake data."""
+import math
+
+import torch
+
+from vit_10b_fsdp_example_b200.config import ViTConfig, parse_args
+from vit_10b_fsdp_example_b200.data import FakeImageNetDataset, build_datasets
+from vit_10b_fsdp_example_b200.utils import SmoothedValue, get_warmup_cosine_scheduler
+
+README_CMD = ("--data_dir /datasets/imagenet-1k --ckpt_dir /tmp/vit_fsdp --image_size 224 --patch_size 14 "
+              "--embed_dim 5120 --mlp_ratio 4.0 --num_heads 32 --num_blocks 32 --batch_size 1024 --num_epochs 300 "
+              "--lr 1e-3 --weight_decay 0.1 --clip_grad_norm 1.0 --warmup_steps 10000 --log_step_interval 20 "
+              "--shard_on_cpu").split()
+
+
+def test_readme_command_line_parses_unchanged():
+    cfg = parse_args(README_CMD)
+    assert cfg.embed_dim == 5120 and cfg.num_blocks == 32 and cfg.shard_on_cpu and cfg.batch_size == 1024
+    assert cfg.grad_ckpt and cfg.reshard_after_forward and not cfg.flatten_parameters and not cfg.run_without_fsdp
+
+
+def test_defaults_are_the_vit10b_recipe():
+    cfg = parse_args([])
+    ref = dict(data_dir="/datasets/imagenet-1k", fake_data=False, num_workers=4, ckpt_dir="/tmp/vit_fsdp",
+               resume_epoch=0, ckpt_epoch_interval=10, test_epoch_interval=10, log_step_interval=20, image_size=224,
+               patch_size=14, embed_dim=5120, num_heads=32, num_blocks=32, mlp_ratio=4.0, pos_dropout=0.0,
+               att_dropout=0.0, mlp_dropout=0.0, num_classes=1000, batch_size=1024, num_epochs=300, lr=1e-3,
+               weight_decay=0.1, clip_grad_norm=1.0, warmup_steps=10000, grad_ckpt=True, reshard_after_forward=True,
+               flatten_parameters=False, run_without_fsdp=False, shard_on_cpu=False)
+    for k, v in ref.items():
+        assert getattr(cfg, k) == v, k
+    flags = parse_args(["--no_grad_ckpt", "--no_reshard_after_forward", "--flatten_parameters", "--run_without_fsdp",
+                        "--fake_data"])
+    assert not flags.grad_ckpt and not flags.reshard_after_forward and flags.flatten_parameters
+    assert flags.run_without_fsdp and flags.fake_data
+    v = ViTConfig.from_args(cfg)
+    assert v.num_patches == 256 and v.head_dim == 160 and v.hidden_dim == 20480
+
+
+def test_warmup_cosine_schedule():
+    class Opt:
+        def __init__(self):
+            self.param_groups = [{"lr": 1e-3}]
+
+    opt = Opt()
+    sched = get_warmup_cosine_scheduler(opt, warmup_iteration=10, max_iteration=110)
+    assert opt.param_groups[0]["lr"] == 0.0
+    for _ in range(5):
+        sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 0.5e-3) < 1e-12
+    for _ in range(5):
+        sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 1e-3) < 1e-12
+    for _ in range(50):
+        sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 1e-3 * 0.5 * (1 + math.cos(math.pi * 0.5))) < 1e-12
+    state = sched.state_dict()
+    opt2 = Opt()
+    s2 = get_warmup_cosine_scheduler(opt2, 10, 110)
+    s2.load_state_dict(state)
+    assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
+
+
+def test_smoothed_value():
+    m = SmoothedValue(window_size=3)
+    for v in [1.0, 2.0, 3.0, 4.0]:
+        m.update(v, batch_size=1)
+    assert m.avg == 3.0 and m.median == 3.0 and m.global_avg == 2.5 and m.get_latest() == 4.0
+
+
+def test_fake_data_pipeline():
+    ds = FakeImageNetDataset(32, 100)
+    img, label = ds[7]
+    assert img.shape == (3, 32, 32) and float(img.abs().sum()) == 0.0 and label == 0 and len(ds) == 100
+    cfg = parse_args(["--fake_data", "--image_size", "32", "--batch_size", "8"])
+    train_ds, train_loader, train_sampler, val_ds, val_loader, _ = build_datasets(cfg, torch.device("cpu"), 2, 1,
+                                                                                 log=lambda *a: None)
+    assert len(train_ds) == 1281167 and len(val_ds) == 50000
+    assert len(train_loader) == (1281167 // 2) // 4
+    data, target = next(iter(train_loader))
+    assert data.shape == (4, 3, 32, 32) and target.shape == (4,) and int(target.sum()) == 0
