@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
     }
     if (warp_idx == 1 && elect_one()) {
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_bar[i], 2);   // leader's expect_tx arrive + peer's plain arrive
+            mbar_init(&full_bar[i], 1);   // leader's expect_tx arrive (covers both CTAs' bytes)
             mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
@@ -167,11 +167,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
                             tma_load_4d_2cta(&tmap_b, &full_bar[stage], sb + i * (64 * kBlockK * 2), n_idx + i * 64,
                                              k_idx, bi, bo);
                     }
-                    if (is_leader) {
-                        mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                    } else {
-                        mbar_arrive_cluster(&full_bar[stage], 0);
-                    }
+                    // Only the leader arms the barrier, for the bytes of BOTH CTAs.  The peer's complete_tx may
+                    // land first (tx-count goes transiently negative, which is legal); it can never leak into
+                    // the next phase because the peer only refills a slot after the MMA that consumed it
+                    // committed.  (A remote arrive here costs a GPU-scope membar per k-block.)
+                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
                     stage = (stage + 1 == kStages) ? 0 : stage + 1;
                     phase ^= (stage == 0);
                 }
@@ -526,7 +526,8 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
                cudaStream_t stream) {
-    if (N % 8 != 0) throw std::runtime_error("gemm: N must be a multiple of 8");
+    if (N % 8 != 0 && (epi.bias || epi.residual || epi.aux_in))
+        throw std::runtime_error("gemm: N must be a multiple of 8 when bias/residual/aux_in are used");
     if (D.nb_inner * D.nb_outer > 1 && (epi.bias || epi.residual || epi.aux_in))
         throw std::runtime_error("gemm: bias/residual/aux_in are not supported for batched problems");
     if (block_n == 0) block_n = (N > 128) ? 256 : 128;

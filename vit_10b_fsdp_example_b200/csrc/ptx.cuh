@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "{\n\t"
         ".reg .b32 raddr;\n\t"
         "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [raddr];\n\t"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");

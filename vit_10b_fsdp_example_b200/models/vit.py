@@ -57,7 +57,7 @@ def logical_shapes(cfg: ViTConfig) -> Dict[str, Tuple[int, ...]]:
     return {"patch_embed.proj.weight": (cfg.embed_dim, 3, P, P), "pos_embed": (1, cfg.num_patches, cfg.embed_dim)}
 
 
-def _linear_init(out_f: int, in_f: int, gen, fan_in: Optional[int] = None):
+def _linear_init(out_f: int, in_f: int, gen, fan_in: Optional[int] = None, device="cpu"):
     """PyTorch's default nn.Linear / nn.Conv2d init (kaiming_uniform a=sqrt(5)): U(+-1/sqrt(fan_in)).
 
     The reference calls timm's ``_init_vit_weights`` on composite modules where it matches nothing
@@ -65,34 +65,34 @@ def _linear_init(out_f: int, in_f: int, gen, fan_in: Optional[int] = None):
     """
     fan_in = fan_in or in_f
     bound = 1.0 / math.sqrt(fan_in)
-    w = (torch.rand(out_f, in_f, generator=gen) * 2.0 - 1.0) * bound
-    b = (torch.rand(out_f, generator=gen) * 2.0 - 1.0) * bound
+    w = (torch.rand(out_f, in_f, generator=gen, device=device) * 2.0 - 1.0) * bound
+    b = (torch.rand(out_f, generator=gen, device=device) * 2.0 - 1.0) * bound
     return w, b
 
 
-def init_block_params(cfg: ViTConfig, gen) -> Dict[str, torch.Tensor]:
+def init_block_params(cfg: ViTConfig, gen, device="cpu") -> Dict[str, torch.Tensor]:
     D, Hd = cfg.embed_dim, cfg.hidden_dim
-    p = {"norm1.weight": torch.ones(D), "norm1.bias": torch.zeros(D),
-         "norm2.weight": torch.ones(D), "norm2.bias": torch.zeros(D)}
-    p["attn.qkv.weight"], p["attn.qkv.bias"] = _linear_init(3 * D, D, gen)
-    p["attn.proj.weight"], p["attn.proj.bias"] = _linear_init(D, D, gen)
-    p["mlp.fc1.weight"], p["mlp.fc1.bias"] = _linear_init(Hd, D, gen)
-    p["mlp.fc2.weight"], p["mlp.fc2.bias"] = _linear_init(D, Hd, gen)
+    p = {"norm1.weight": torch.ones(D, device=device), "norm1.bias": torch.zeros(D, device=device),
+         "norm2.weight": torch.ones(D, device=device), "norm2.bias": torch.zeros(D, device=device)}
+    p["attn.qkv.weight"], p["attn.qkv.bias"] = _linear_init(3 * D, D, gen, device=device)
+    p["attn.proj.weight"], p["attn.proj.bias"] = _linear_init(D, D, gen, device=device)
+    p["mlp.fc1.weight"], p["mlp.fc1.bias"] = _linear_init(Hd, D, gen, device=device)
+    p["mlp.fc2.weight"], p["mlp.fc2.bias"] = _linear_init(D, Hd, gen, device=device)
     return p
 
 
-def init_root_params(cfg: ViTConfig, gen) -> Dict[str, torch.Tensor]:
+def init_root_params(cfg: ViTConfig, gen, device="cpu") -> Dict[str, torch.Tensor]:
     D = cfg.embed_dim
     p = {}
-    w, b = _linear_init(D, cfg.patch_k, gen)
-    wp = torch.zeros(D, cfg.patch_kpad)
+    w, b = _linear_init(D, cfg.patch_k, gen, device=device)
+    wp = torch.zeros(D, cfg.patch_kpad, device=device)
     wp[:, : cfg.patch_k] = w
     p["patch_embed.proj.weight"], p["patch_embed.proj.bias"] = wp, b
-    pos = torch.empty(cfg.num_patches, D)
+    pos = torch.empty(cfg.num_patches, D, device=device)
     torch.nn.init.trunc_normal_(pos, std=0.02, generator=gen)  # run_vit_training.py:128
     p["pos_embed"] = pos
-    p["norm.weight"], p["norm.bias"] = torch.ones(D), torch.zeros(D)
-    p["head.weight"], p["head.bias"] = _linear_init(cfg.num_classes, D, gen)
+    p["norm.weight"], p["norm.bias"] = torch.ones(D, device=device), torch.zeros(D, device=device)
+    p["head.weight"], p["head.bias"] = _linear_init(cfg.num_classes, D, gen, device=device)
     return p
 
 
