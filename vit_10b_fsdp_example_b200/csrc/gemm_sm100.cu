@@ -526,8 +526,8 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
                cudaStream_t stream) {
-    if (N % 8 != 0 && (epi.bias || epi.residual || epi.aux_in))
-        throw std::runtime_error("gemm: N must be a multiple of 8 when bias/residual/aux_in are used");
+    if (N % 8 != 0 && (epi.residual || epi.aux_in))
+        throw std::runtime_error("gemm: N must be a multiple of 8 when residual/aux_in are used");
     if (D.nb_inner * D.nb_outer > 1 && (epi.bias || epi.residual || epi.aux_in))
         throw std::runtime_error("gemm: bias/residual/aux_in are not supported for batched problems");
     if (block_n == 0) block_n = (N > 128) ? 256 : 128;

@@ -65,6 +65,30 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _tma_rows(t: torch.Tensor) -> torch.Tensor:
+    """TMA needs 16-byte row strides and base.  Matrices whose width is not a multiple of 8 (e.g. a classifier
+    with an odd class count) are copied into a zero-padded buffer and used through a strided view."""
+    if t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    rows, cols = t.shape
+    buf = torch.zeros(rows, _pad8(cols), dtype=t.dtype, device=t.device)
+    buf[:, :cols].copy_(t)
+    return buf[:, :cols]
+
+
+def _bias_ok(b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The epilogue reads bias in 16-byte vectors: pad odd-length biases so the tail read stays in bounds."""
+    if b is None or b.numel() % 8 == 0:
+        return b
+    buf = torch.zeros(_pad8(b.numel()), dtype=b.dtype, device=b.device)
+    buf[: b.numel()].copy_(b)
+    return buf
+
+
 def gemm_raw(a, lda, major_a, b, ldb, major_b, d, ldd, M, N, K, *, bias=None, residual=None, ld_res=0,
              res_row_mod=0, aux_in=None, ld_aux=0, aux_out=None, ld_aux_out=0, colsum=None, colsum_bi_stride=0,
              act=ACT_NONE, batch=(), block_n=0, max_ctas=None):
@@ -100,17 +124,23 @@ def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_ro
                want_preact: bool = False):
     M, K = x.shape
     N = w.shape[0]
-    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
-    pre = torch.empty(M, N, dtype=x.dtype, device=x.device) if want_preact else None
-    gemm_raw(x, _ld(x), 0, w, _ld(w), 0, y, N, M, N, K, bias=bias, residual=residual,
+    x, w = _tma_rows(x), _tma_rows(w)
+    ldy = _pad8(N)
+    y = torch.empty(M, ldy, dtype=x.dtype, device=x.device)
+    pre = torch.empty(M, ldy, dtype=x.dtype, device=x.device) if want_preact else None
+    gemm_raw(x, _ld(x), 0, w, _ld(w), 0, y, ldy, M, N, K, bias=_bias_ok(bias), residual=residual,
              ld_res=_ld(residual) if residual is not None else 0, res_row_mod=res_row_mod, aux_out=pre,
-             ld_aux_out=N, act=ACT_GELU if act == "gelu" else ACT_NONE)
+             ld_aux_out=ldy, act=ACT_GELU if act == "gelu" else ACT_NONE)
+    if ldy != N:
+        y = y[:, :N].contiguous()
+        pre = pre[:, :N].contiguous() if pre is not None else None
     return (y, pre) if want_preact else y
 
 
 def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
     M, N = dy.shape
     K = w.shape[1]
+    dy, w = _tma_rows(dy), _tma_rows(w)
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
     cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if want_colsum else None
     gemm_raw(dy, _ld(dy), 0, w, _ld(w), 1, dx, K, M, K, N, aux_in=dgelu_preact,
@@ -122,6 +152,7 @@ def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
 def linear_wgrad(dy, x, out=None):
     T, N = dy.shape
     K = x.shape[1]
+    dy, x = _tma_rows(dy), _tma_rows(x)
     if out is None:
         out = torch.empty(N, K, dtype=dy.dtype, device=dy.device)
     gemm_raw(dy, _ld(dy), 1, x, _ld(x), 1, out, _ld(out), N, K, T)
@@ -137,10 +168,6 @@ def colsum(x):
 # ------------------------------------------------------------------------------------------------
 # Attention core
 # ------------------------------------------------------------------------------------------------
-def _pad8(n: int) -> int:
-    return (n + 7) // 8 * 8
-
-
 def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0):
     if drop_mask is not None:  # attention dropout > 0: rare path, run the reference math
         return torch_ops.attention_fwd(qkv, B, N, H, hd, drop_mask, drop_scale)

@@ -110,11 +110,15 @@ class Sm100Backend(TorchDistBackend):
     def __init__(self, world: int, rank: int, device: torch.device, comm_ctas: int = 24):
         super().__init__(world, rank, device)
         from ..ops import native
-        import torch.distributed._symmetric_memory as symm_mem
 
         self._C = native.load()
-        self._symm = symm_mem
         self.comm_ctas = comm_ctas
+        self.use_nvls = False
+        if world == 1:  # single GPU: nothing to communicate, gathered buffers alias the shards
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._symm = symm_mem
         self._handles = []   # keep rendezvous handles alive
         self._peer = {}      # data_ptr of a symmetric tensor -> list of peer base pointers
         self._mc = {}        # data_ptr -> multicast base pointer (0 if unsupported)
@@ -146,11 +150,15 @@ class Sm100Backend(TorchDistBackend):
         return t
 
     def alloc_shard(self, numel: int, dtype) -> torch.Tensor:
+        if self.world == 1:
+            return super().alloc_shard(numel, dtype)
         t = self._symm_alloc(numel, dtype)
         t.zero_()
         return t
 
     def alloc_full_grad(self, numel: int, dtype) -> torch.Tensor:
+        if self.world == 1:
+            return super().alloc_full_grad(numel, dtype)
         t = self._symm_alloc(numel, dtype)
         t.zero_()
         return t
