@@ -1,0 +1,167 @@
+"""Multi-GPU tests of the NVLink symmetric-memory collectives and the sm100 FSDP backend.
+
+Needs >= 2 GPUs (skipped otherwise): `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`.
+Custom all-gather must be bit-exact vs NCCL; reduce-scatter within fp32 reorder tolerance; flags are reused
+for >= 1000 iterations to catch phase bugs.
+"""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _need_gpus(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _init(rank, world, port):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    return dist
+
+
+def _collectives_worker(rank, world, port, out_path):
+    dist = _init(rank, world, port)
+    from vit_10b_fsdp_example_b200.config import ViTConfig
+    from vit_10b_fsdp_example_b200.models import vit
+    from vit_10b_fsdp_example_b200.ops import cuda_ops
+    from vit_10b_fsdp_example_b200.parallel.backends import Sm100Backend, TorchDistBackend
+    from vit_10b_fsdp_example_b200.parallel.layout import UnitLayout
+
+    dev = torch.device("cuda", rank)
+    sm = Sm100Backend(world, rank, dev)
+    nc = TorchDistBackend(world, rank, dev)
+    res = {"nvls": bool(sm.use_nvls)}
+    cfg = ViTConfig(embed_dim=640, num_heads=4, num_blocks=1)
+    for flatten in (False, True):
+        lay = UnitLayout.build("blocks.0", vit.block_param_specs(cfg), world, flatten)
+        torch.manual_seed(100 + rank)
+        shard = sm.alloc_shard(lay.shard_numel, torch.bfloat16)
+        shard.copy_(torch.randn(lay.shard_numel, device=dev))
+        sm.params_updated()
+        full_a = torch.zeros(lay.full_numel, dtype=torch.bfloat16, device=dev)
+        full_b = torch.zeros(lay.full_numel, dtype=torch.bfloat16, device=dev)
+        sm.all_gather(lay, shard, full_a)
+        nc.all_gather(lay, shard, full_b)
+        torch.cuda.synchronize()
+        res[f"ag_exact_{int(flatten)}"] = bool(torch.equal(full_a, full_b))
+        # reduce-scatter: P2P and (if available) NVLS vs NCCL fp32
+        grad = sm.alloc_full_grad(lay.full_numel, torch.bfloat16)
+        grad.copy_(torch.randn(lay.full_numel, device=dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        ref = torch.zeros(lay.shard_numel, dtype=torch.float32, device=dev)
+        ssq_ref = torch.zeros(1, device=dev)
+        nc.reduce_scatter(lay, grad, ref, ssq_ref, cuda_ops)
+        for mode in ("p2p", "nvls"):
+            if mode == "nvls" and not sm.use_nvls:
+                continue
+            saved = sm.use_nvls
+            sm.use_nvls = mode == "nvls"
+            out = torch.zeros(lay.shard_numel, dtype=torch.float32, device=dev)
+            ssq = torch.zeros(1, device=dev)
+            sm.reduce_scatter(lay, grad, out, ssq, cuda_ops)
+            torch.cuda.synchronize()
+            sm.use_nvls = saved
+            tol = 1e-6 if mode == "p2p" else 2e-2  # NVLS returns the fp32 sum rounded to bf16
+            err = (out - ref).abs().max().item()
+            res[f"rs_{mode}_err_{int(flatten)}"] = err
+            res[f"rs_{mode}_ok_{int(flatten)}"] = bool(err <= tol * (ref.abs().max().item() + 1e-6) + 1e-7)
+            res[f"rs_{mode}_ssq_ok_{int(flatten)}"] = bool(abs(ssq.item() - ssq_ref.item()) <= 2e-2 * ssq_ref.item())
+    # scalar all-reduce + barrier reuse for > 1000 iterations (sequence-number / phase bugs)
+    ok = True
+    for it in range(1100):
+        v = torch.tensor([float(rank + it), 1.0], device=dev)
+        sm.all_reduce_scalars_(v, "sum")
+        if it % 97 == 0:
+            sm.device_barrier(0)
+        if it % 100 == 0 or it == 1099:
+            exp = sum(r + it for r in range(world))
+            ok = ok and abs(v[0].item() - exp) < 1e-3 and abs(v[1].item() - world) < 1e-6
+    m = torch.tensor([float(rank)], device=dev)
+    sm.all_reduce_scalars_(m, "max")
+    res["scalars_ok"] = bool(ok and m.item() == world - 1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        json.dump(res, open(out_path, "w"))
+    dist.destroy_process_group()
+
+
+def _train_worker(rank, world, port, backend, out_path, flatten, reshard):
+    dist = _init(rank, world, port)
+    from vit_10b_fsdp_example_b200.config import ViTConfig
+    from vit_10b_fsdp_example_b200.parallel import FSDPViT, ShardedAdamW
+
+    dev = torch.device("cuda", rank)
+    cfg = ViTConfig(image_size=112, patch_size=14, embed_dim=320, num_heads=2, num_blocks=3, mlp_ratio=4.0,
+                    num_classes=96)
+    model = FSDPViT(cfg, world=world, rank=rank, device=dev, dtype=torch.bfloat16, backend=backend, seed=1,
+                    flatten_parameters=flatten, reshard_after_forward=reshard)
+    opt = ShardedAdamW(model, lr=1e-3, weight_decay=0.1)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(8, 3, 112, 112, generator=g)
+    target = torch.randint(0, 96, (8,), generator=g)
+    lb = 8 // world
+    losses, norms = [], []
+    for _ in range(6):
+        loss = model.forward_backward(images[rank * lb:(rank + 1) * lb].to(dev), target[rank * lb:(rank + 1) * lb].to(dev))
+        norm = model.clip_grad_norm_(1.0)
+        opt.step()
+        lv = loss.detach().float().reshape(1).clone()
+        dist.all_reduce(lv)
+        losses.append(lv.item() / world)
+        norms.append(norm.item())
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        json.dump({"losses": losses, "norms": norms}, open(out_path, "w"))
+    dist.destroy_process_group()
+
+
+def _spawn(fn, world, args):
+    import torch.multiprocessing as mp
+    from helpers import free_port
+
+    mp.spawn(fn, args=(world, free_port()) + args, nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world", [2])
+def test_symmetric_memory_collectives(world, tmp_path):
+    _need_gpus(world)
+    out = str(tmp_path / "c.json")
+    _spawn(_collectives_worker, world, (out,))
+    res = json.load(open(out))
+    print(res)
+    bad = [k for k, v in res.items() if k.endswith(("_ok_0", "_ok_1", "exact_0", "exact_1", "scalars_ok")) and not v]
+    assert not bad, (bad, res)
+
+
+@pytest.mark.parametrize("flatten,reshard", [(False, True), (True, False)])
+def test_sm100_backend_matches_nccl_backend(flatten, reshard, tmp_path):
+    world = 2
+    _need_gpus(world)
+    outs = {}
+    for backend in ("torchdist", "sm100"):
+        out = str(tmp_path / f"{backend}.json")
+        _spawn(_train_worker, world, (backend, out, flatten, reshard))
+        outs[backend] = json.load(open(out))
+    a, b = outs["torchdist"], outs["sm100"]
+    for x, y in zip(a["losses"], b["losses"]):
+        assert abs(x - y) < 0.03 * abs(x) + 0.02, (a, b)
+    for x, y in zip(a["norms"], b["norms"]):
+        assert abs(x - y) < 0.05 * abs(x) + 0.02, (a, b)
+    assert b["losses"][-1] < b["losses"][0]
