@@ -46,3 +46,18 @@ def test_vit10b_block_layout_numbers():
     assert lay.payload_numel() == cfg.block_numel()
     assert lay.shard_numel * 8 == lay.full_numel
     assert lay.full_numel - cfg.block_numel() < 12 * 8 * ALIGN
+
+
+def test_split_fp32_is_exact_including_ties():
+    """(bf16 hi, int16 lo) must reproduce every fp32 bit pattern, also exact rounding ties and negatives."""
+    from vit_10b_fsdp_example_b200.ops import torch_ops
+
+    bits = torch.tensor([0x3F808000, 0x3F818000, 0xBF808000, 0xBF818000, 0x3F807FFF, 0x3F808001, 0x00000000,
+                         0x80000000, 0x3F7FFFFF, 0x7F7FFFFF], dtype=torch.int64).to(torch.int32)
+    w = torch.cat([bits.view(torch.float32), torch.randn(4096)])
+    hi = torch.empty(w.numel(), dtype=torch.bfloat16)
+    lo = torch.empty(w.numel(), dtype=torch.int16)
+    torch_ops.split_fp32(w, hi, lo)
+    back = torch.empty_like(w)
+    torch_ops.merge_fp32(hi, lo, back)
+    assert torch.equal(back.view(torch.int32), w.view(torch.int32))

@@ -439,6 +439,16 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, int
 // tensor the next all-gather ships and the GEMMs consume), `lo` is the signed 16-bit remainder so that
 // (hi << 16) + lo reproduces the fp32 bits exactly.  No separate bf16 copy, no extra cast pass.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_grad4(const float* g, int64_t i, float (&out)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i);
+    out[0] = v.x, out[1] = v.y, out[2] = v.z, out[3] = v.w;
+}
+__device__ __forceinline__ void load_grad4(const __nv_bfloat16* g, int64_t i, float (&out)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(g + i);
+    out[0] = bf16_lo(v.x), out[1] = bf16_hi(v.x), out[2] = bf16_lo(v.y), out[3] = bf16_hi(v.y);
+}
+
+// 4 elements per thread: 8 B (hi) + 8 B (lo) + 16 B (m) + 16 B (v) + 8/16 B (grad) vector accesses.
 template <typename GradT>
 __global__ void __launch_bounds__(256) adamw_split_kernel(uint16_t* __restrict__ hi, int16_t* __restrict__ lo,
                                                           float* __restrict__ m, float* __restrict__ v,
@@ -446,21 +456,53 @@ __global__ void __launch_bounds__(256) adamw_split_kernel(uint16_t* __restrict__
                                                           const float* __restrict__ clip_coef, float lr, float beta1,
                                                           float beta2, float eps, float wd, float bc1, float bc2) {
     const float coef = clip_coef != nullptr ? *clip_coef : 1.0f;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+    const float inv_bc1 = 1.f / bc1, inv_bc2 = 1.f / bc2, decay = 1.f - lr * wd;
+    const int64_t n4 = n / 4;
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n4;
+         q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t i = q * 4;
+        const uint2 hv = *reinterpret_cast<const uint2*>(hi + i);
+        const uint2 lv = *reinterpret_cast<const uint2*>(lo + i);
+        float4 mv = *reinterpret_cast<const float4*>(m + i);
+        float4 vv = *reinterpret_cast<const float4*>(v + i);
+        float g[4];
+        load_grad4(grad, i, g);
+        const uint32_t hw[4] = {hv.x & 0xFFFFu, hv.x >> 16, hv.y & 0xFFFFu, hv.y >> 16};
+        const uint32_t lw[4] = {lv.x & 0xFFFFu, lv.x >> 16, lv.y & 0xFFFFu, lv.y >> 16};
+        float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vq[4] = {vv.x, vv.y, vv.z, vv.w};
+        uint32_t ho[4], lo_o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int32_t bits = static_cast<int32_t>(hw[k] << 16) + static_cast<int32_t>(static_cast<int16_t>(lw[k]));
+            float w = __int_as_float(bits);
+            const float gk = g[k] * coef;
+            mm[k] = beta1 * mm[k] + (1.f - beta1) * gk;
+            vq[k] = beta2 * vq[k] + (1.f - beta2) * gk * gk;
+            w = w * decay - lr * (mm[k] * inv_bc1) / (sqrtf(vq[k] * inv_bc2) + eps);
+            const int32_t nb = __float_as_int(w);
+            const int32_t rounded = nb + 0x8000;  // round-half-up: keeps lo in [-32768, 32767] (see split_fp32)
+            const int32_t h = rounded >> 16;
+            ho[k] = static_cast<uint32_t>(h) & 0xFFFFu;
+            lo_o[k] = static_cast<uint32_t>(nb - (h << 16)) & 0xFFFFu;
+        }
+        *reinterpret_cast<uint2*>(hi + i) = make_uint2(ho[0] | (ho[1] << 16), ho[2] | (ho[3] << 16));
+        *reinterpret_cast<uint2*>(lo + i) = make_uint2(lo_o[0] | (lo_o[1] << 16), lo_o[2] | (lo_o[3] << 16));
+        *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        *reinterpret_cast<float4*>(v + i) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    }
+    // scalar tail (n not a multiple of 4)
+    for (int64_t i = n4 * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int32_t bits = (static_cast<int32_t>(hi[i]) << 16) + static_cast<int32_t>(lo[i]);
         float w = __int_as_float(bits);
-        const float g = static_cast<float>(grad[i]) * coef;
-        const float mi = beta1 * m[i] + (1.f - beta1) * g;
-        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        const float gk = static_cast<float>(grad[i]) * coef;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gk;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gk * gk;
         m[i] = mi;
         v[i] = vi;
-        const float mhat = mi / bc1;
-        const float vhat = vi / bc2;
-        w = w * (1.f - lr * wd) - lr * mhat / (sqrtf(vhat) + eps);
+        w = w * decay - lr * (mi * inv_bc1) / (sqrtf(vi * inv_bc2) + eps);
         const int32_t nb = __float_as_int(w);
-        // round-to-nearest-even bf16 in integer arithmetic (weights are finite)
-        const int32_t rounded = nb + 0x7FFF + ((nb >> 16) & 1);
+        const int32_t rounded = nb + 0x8000;
         const int32_t h = rounded >> 16;
         hi[i] = static_cast<uint16_t>(h & 0xFFFF);
         lo[i] = static_cast<int16_t>(nb - (h << 16));
@@ -492,7 +534,7 @@ __global__ void split_fp32_kernel(const float* __restrict__ w, uint16_t* __restr
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int32_t nb = __float_as_int(w[i]);
-        const int32_t rounded = nb + 0x7FFF + ((nb >> 16) & 1);
+        const int32_t rounded = nb + 0x8000;
         const int32_t h = rounded >> 16;
         hi[i] = static_cast<uint16_t>(h & 0xFFFF);
         lo[i] = static_cast<int16_t>(nb - (h << 16));
@@ -623,7 +665,7 @@ void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stre
 void adamw_split(uint16_t* hi, int16_t* lo, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n,
                  const float* clip_coef, float lr, float beta1, float beta2, float eps, float wd, int step,
                  cudaStream_t stream) {
-    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, sm_count() * 16));
+    const int grid = static_cast<int>(std::min<int64_t>((n / 4 + 255) / 256 + 1, sm_count() * 16));
     if (grid == 0) return;
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));

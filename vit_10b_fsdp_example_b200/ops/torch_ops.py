@@ -198,10 +198,11 @@ def adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
     w.addcdiv_(m / bc1, denom, value=-lr)
 
 
-# Split fp32 master representation: fp32 bits == (hi_bf16_bits << 16) + lo_int16, hi = RN-even bf16.
+# Split fp32 master representation: fp32 bits == (hi_bf16_bits << 16) + lo_int16, hi = nearest bf16
+# (ties round up in the bit pattern so that lo always fits a signed 16-bit integer).
 def split_fp32(w, hi, lo):
     bits = w.contiguous().view(torch.int32)
-    rounded = bits + 0x7FFF + ((bits >> 16) & 1)
+    rounded = bits + 0x8000  # round-half-up keeps lo within int16 for every input (ties included)
     h = rounded >> 16
     hi.copy_((h << 16).view(torch.float32).to(torch.bfloat16))
     lo.copy_((bits - (h << 16)).to(torch.int16))
