@@ -138,33 +138,30 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __nv_bfloat16*
 // LayerNorm backward.  dx = [dres +] rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; optionally dxsum += sum_rows dx
 // (the latter is the bias gradient of the Linear that produced x's residual branch).
+// A thread always owns the same columns, so the per-CTA column accumulators live in shared memory
+// (plain read-modify-write, no atomics) instead of ~100 registers: 3 CTAs/SM stay resident and keep
+// enough loads in flight to stream at HBM speed.
 // ------------------------------------------------------------------------------------------------
 template <int kChunks>
-__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ x,
-                                                            const __nv_bfloat16* __restrict__ gamma,
-                                                            const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in,
-                                                            const __nv_bfloat16* __restrict__ dres,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ dxsum,
-                                                            int rows, int D) {
+__global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ gamma,
+                                                               const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in,
+                                                               const __nv_bfloat16* __restrict__ dres,
+                                                               __nv_bfloat16* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               float* __restrict__ dxsum, int rows, int D) {
     __shared__ float red[64];
+    extern __shared__ __align__(16) float acc[];  // [dg | db | dxs] each D floats
+    float* acc_dg = acc;
+    float* acc_db = acc + D;
+    float* acc_dx = acc + 2 * D;
     const int nvec = D / 8;
     const float inv_d = 1.0f / static_cast<float>(D);
-    float gam[kChunks][8], dg[kChunks][8], db[kChunks][8], dxs[kChunks][8];
-#pragma unroll
-    for (int i = 0; i < kChunks; ++i) {
-        const int idx = threadIdx.x + i * kLnThreads;
-        if (idx < nvec) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), gam[i]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) gam[i][q] = 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dg[i][q] = 0.f, db[i][q] = 0.f, dxs[i][q] = 0.f;
-    }
+    const int narr = dxsum != nullptr ? 3 : 2;
+    for (int i = threadIdx.x; i < narr * D; i += kLnThreads) acc[i] = 0.f;
+    __syncthreads();
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int64_t base = static_cast<int64_t>(row) * D;
         const uint4* xr = reinterpret_cast<const uint4*>(x + base);
@@ -182,18 +179,28 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const __nv_bfloat16*
         for (int i = 0; i < kChunks; ++i) {
             const int idx = threadIdx.x + i * kLnThreads;
             if (idx < nvec) {
-                float xf[8], df[8];
+                float xf[8], df[8], gf[8];
                 unpack8(xv[i], xf);
                 unpack8(dv[i], df);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), gf);
+                float4* pg = reinterpret_cast<float4*>(acc_dg + idx * 8);
+                float4* pb = reinterpret_cast<float4*>(acc_db + idx * 8);
+                float4 g0 = pg[0], g1 = pg[1], b0 = pb[0], b1 = pb[1];
+                float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                float ba[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float xhat = (xf[q] - mean) * rstd;
-                    const float g = df[q] * gam[i][q];
+                    const float g = df[q] * gf[q];
                     s1 += g;
                     s2 += g * xhat;
-                    dg[i][q] += df[q] * xhat;
-                    db[i][q] += df[q];
+                    ga[q] += df[q] * xhat;
+                    ba[q] += df[q];
                 }
+                pg[0] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+                pg[1] = make_float4(ga[4], ga[5], ga[6], ga[7]);
+                pb[0] = make_float4(ba[0], ba[1], ba[2], ba[3]);
+                pb[1] = make_float4(ba[4], ba[5], ba[6], ba[7]);
             }
         }
         block_sum2<kLnThreads>(s1, s2, red);
@@ -204,9 +211,10 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const __nv_bfloat16*
         for (int i = 0; i < kChunks; ++i) {
             const int idx = threadIdx.x + i * kLnThreads;
             if (idx < nvec) {
-                float xf[8], df[8], rf[8], o[8];
+                float xf[8], df[8], gf[8], rf[8], o[8];
                 unpack8(xv[i], xf);
                 unpack8(dv[i], df);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), gf);
                 if (dres != nullptr) {
                     unpack8(reinterpret_cast<const uint4*>(dres + base)[idx], rf);
                 } else {
@@ -216,28 +224,31 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const __nv_bfloat16*
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float xhat = (xf[q] - mean) * rstd;
-                    o[q] = rf[q] + rstd * (df[q] * gam[i][q] - s1 - xhat * s2);
+                    o[q] = rf[q] + rstd * (df[q] * gf[q] - s1 - xhat * s2);
                 }
                 const uint4 packed = pack8(o);
                 dxr[idx] = packed;
                 if (dxsum != nullptr) {
                     float ob[8];
                     unpack8(packed, ob);  // sum what was actually stored (bf16-rounded), like a torch .sum(0)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) dxs[i][q] += ob[q];
+                    float4* px = reinterpret_cast<float4*>(acc_dx + idx * 8);
+                    float4 a0 = px[0], a1 = px[1];
+                    px[0] = make_float4(a0.x + ob[0], a0.y + ob[1], a0.z + ob[2], a0.w + ob[3]);
+                    px[1] = make_float4(a1.x + ob[4], a1.y + ob[5], a1.z + ob[6], a1.w + ob[7]);
                 }
             }
         }
     }
+    // own columns only -> no intra-CTA hazard; one global atomic per column per CTA
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
         const int idx = threadIdx.x + i * kLnThreads;
         if (idx < nvec) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                atomicAdd(dgamma + idx * 8 + q, dg[i][q]);
-                atomicAdd(dbeta + idx * 8 + q, db[i][q]);
-                if (dxsum != nullptr) atomicAdd(dxsum + idx * 8 + q, dxs[i][q]);
+                atomicAdd(dgamma + idx * 8 + q, acc_dg[idx * 8 + q]);
+                atomicAdd(dbeta + idx * 8 + q, acc_db[idx * 8 + q]);
+                if (dxsum != nullptr) atomicAdd(dxsum + idx * 8 + q, acc_dx[idx * 8 + q]);
             }
         }
     }
@@ -591,13 +602,34 @@ void layernorm_fwd(const __nv_bfloat16* x, const __nv_bfloat16* gamma, const __n
     check_launch("layernorm_fwd");
 }
 
+template <int kChunks>
+void launch_ln_bwd(int grid, size_t smem, cudaStream_t stream, const __nv_bfloat16* dy, const __nv_bfloat16* x,
+                   const __nv_bfloat16* gamma, const float* mean, const float* rstd, const __nv_bfloat16* dres,
+                   __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int D) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(ln_bwd_kernel<kChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        configured = smem;
+    }
+    ln_bwd_kernel<kChunks><<<grid, kLnThreads, smem, stream>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum,
+                                                             rows, D);
+}
+
 void layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const __nv_bfloat16* gamma, const float* mean,
                    const float* rstd, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                    float* dxsum, int rows, int D, cudaStream_t stream) {
     if (D % 8 != 0) throw std::runtime_error("layernorm: width must be a multiple of 8");
     const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
-    const int grid = std::min(rows, sm_count() * 2);
-    LN_DISPATCH(chunks, ln_bwd_kernel, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D);
+    const size_t smem = static_cast<size_t>(dxsum != nullptr ? 3 : 2) * D * sizeof(float);
+    const int per_sm = std::max<int>(1, std::min<int>(3, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
+    const int grid = std::min(rows, sm_count() * per_sm);
+    switch (chunks) {
+        case 1: launch_ln_bwd<1>(grid, smem, stream, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D); break;
+        case 2: launch_ln_bwd<2>(grid, smem, stream, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D); break;
+        case 3: launch_ln_bwd<3>(grid, smem, stream, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D); break;
+        case 4: launch_ln_bwd<4>(grid, smem, stream, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D); break;
+        default: throw std::runtime_error("layernorm: width > 8192 not supported");
+    }
     check_launch("layernorm_bwd");
 }
 
