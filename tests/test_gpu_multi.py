@@ -81,6 +81,29 @@ def _collectives_worker(rank, world, port, out_path):
             res[f"rs_{mode}_err_{int(flatten)}"] = err
             res[f"rs_{mode}_ok_{int(flatten)}"] = bool(err <= tol * (ref.abs().max().item() + 1e-6) + 1e-7)
             res[f"rs_{mode}_ssq_ok_{int(flatten)}"] = bool(abs(ssq.item() - ssq_ref.item()) <= 2e-2 * ssq_ref.item())
+    # all-gather fused into the consuming GEMM: y = x @ W^T where W's row slabs live on the peers
+    Nw, Kw, Mx = 2048, 512, 1024
+    torch.manual_seed(7)
+    w_full = (torch.randn(Nw, Kw, device=dev) * 0.05).to(torch.bfloat16)   # identical on every rank (same seed)
+    rows = Nw // world
+    w_shard = sm.alloc_shard(rows * Kw, torch.bfloat16)
+    w_shard.copy_(w_full[rank * rows:(rank + 1) * rows].reshape(-1))
+    sm.params_updated()
+    torch.cuda.synchronize()
+    dist.barrier()
+    xin = torch.randn(Mx, Kw, device=dev).to(torch.bfloat16)
+    bias = torch.randn(Nw, device=dev).to(torch.bfloat16)
+    ref = cuda_ops.linear_fwd(xin, w_full, bias)
+    flags = torch.zeros(16, dtype=torch.int32, device=dev)
+    ok_fused = True
+    for it in range(5):
+        gathered = torch.zeros(Nw, Kw, dtype=torch.bfloat16, device=dev)
+        spec = [world, rank, rows, rows * Kw * 2, gathered.data_ptr(), flags.data_ptr()] + list(sm._peer[w_shard.data_ptr()])
+        y = cuda_ops.linear_fwd(xin, gathered, bias, ag=spec)
+        torch.cuda.synchronize()
+        ok_fused = ok_fused and bool(torch.equal(gathered, w_full)) and bool(torch.equal(y, ref))
+    res["ag_fused_gemm_exact"] = ok_fused
+    dist.barrier()
     # scalar all-reduce + barrier reuse for > 1000 iterations (sequence-number / phase bugs)
     ok = True
     for it in range(1100):
@@ -146,7 +169,8 @@ def test_symmetric_memory_collectives(world, tmp_path):
     _spawn(_collectives_worker, world, (out,))
     res = json.load(open(out))
     print(res)
-    bad = [k for k, v in res.items() if k.endswith(("_ok_0", "_ok_1", "exact_0", "exact_1", "scalars_ok")) and not v]
+    bad = [k for k, v in res.items()
+           if k.endswith(("_ok_0", "_ok_1", "exact_0", "exact_1", "scalars_ok", "ag_fused_gemm_exact")) and not v]
     assert not bad, (bad, res)
 
 

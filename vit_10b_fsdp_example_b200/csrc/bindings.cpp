@@ -32,7 +32,7 @@ inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().strea
 void gemm(Tensor a, int64_t lda, int64_t major_a, Tensor b, int64_t ldb, int64_t major_b, Tensor d, int64_t ldd,
           int64_t M, int64_t N, int64_t K, OptT bias, OptT residual, int64_t ld_res, int64_t res_row_mod, OptT aux_in,
           int64_t ld_aux, OptT aux_out, int64_t ld_aux_out, OptT colsum, int64_t colsum_bi_stride, int64_t act,
-          std::vector<int64_t> batch, int64_t block_n, int64_t max_ctas) {
+          std::vector<int64_t> batch, int64_t block_n, int64_t max_ctas, std::vector<int64_t> ag) {
     c10::cuda::CUDAGuard guard(a.device());
     b200::GemmOperand A, B, D, X;
     A.ptr = bf16_ptr(a), A.ld = lda;
@@ -57,8 +57,17 @@ void gemm(Tensor a, int64_t lda, int64_t major_a, Tensor b, int64_t ldb, int64_t
         X.ptr = bf16_ptr(*aux_out), X.ld = ld_aux_out;
         e.has_aux_out = 1;
     }
+    // ag = [] or [world, rank, rows_per_slab, slab_bytes, dst_ptr, flags_ptr, peer_src_0, ..., peer_src_{W-1}]
+    b200::GemmAgFuse fuse;
+    if (!ag.empty()) {
+        TORCH_CHECK(ag.size() >= 6 && (int64_t)ag.size() == 6 + ag[0] && ag[0] <= 16, "bad AG-fusion spec");
+        fuse.world = (int)ag[0], fuse.rank = (int)ag[1], fuse.rows_per_slab = (int)ag[2], fuse.slab_bytes = ag[3];
+        fuse.dst = reinterpret_cast<void*>(ag[4]);
+        fuse.flags = reinterpret_cast<uint32_t*>(ag[5]);
+        for (int64_t r = 0; r < ag[0]; ++r) fuse.peer_src[r] = static_cast<uint64_t>(ag[6 + r]);
+    }
     b200::gemm_bf16(A, (int)major_a, B, (int)major_b, D, aux_out.has_value() ? &X : nullptr, (int)M, (int)N, (int)K, e,
-                    (int)block_n, (int)max_ctas, cur_stream());
+                    (int)block_n, (int)max_ctas, cur_stream(), ag.empty() ? nullptr : &fuse);
 }
 
 void layernorm_fwd(Tensor x, Tensor gamma, Tensor beta, Tensor y, Tensor mean, Tensor rstd, double eps) {

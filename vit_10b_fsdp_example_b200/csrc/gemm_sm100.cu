@@ -48,8 +48,30 @@ struct KernelParams {
     int M, N, K;
     int batch, nb_inner;
     int m_tiles, n_tiles;  // cluster tiles (256 x BLOCK_N)
+    int n_rot;             // n-tile rotation so that tiles are visited in slab-arrival order (AG fusion)
     GemmEpilogue epi;
+    GemmAgFuse ag;
 };
+
+constexpr int kAgChunkBytes = 16384;
+
+__device__ __forceinline__ uint4 ld_peer_v4(const void* ptr) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(ptr)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* ptr, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): 1 rcp + 1 exp + 6 FMA.
 // e = exp(-z^2) is returned too: for z = x/sqrt(2) it is exactly the Gaussian factor gelu'(x) needs.
@@ -150,7 +172,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
         const int in_g = r - g * per_group;
         mt = in_g / gsz;
         nt = first_n + in_g % gsz;
+        nt += p.n_rot;  // AG fusion: start with the n-tiles of the locally owned slab
+        if (nt >= p.n_tiles) nt -= p.n_tiles;
     };
+    const int ag_chunks_per_slab =
+        p.ag.world > 1 ? static_cast<int>((p.ag.slab_bytes + kAgChunkBytes - 1) / kAgChunkBytes) : 0;
 
     if (warp_idx == 0) {
         // ================================= TMA producer =================================
@@ -162,6 +188,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
                 const int bi = b % p.nb_inner, bo = b / p.nb_inner;
                 const int m_idx = mt * (2 * kBlockM) + cta_rank * kBlockM;
                 const int n_idx = nt * BLOCK_N + cta_rank * LOAD_N;
+                if (p.ag.world > 1) {
+                    // B rows [n_idx, n_idx + LOAD_N) must have been pulled into the local gathered buffer
+                    const int last_row = min(n_idx + LOAD_N, p.N) - 1;
+                    if (last_row >= n_idx) {
+                        const int s_lo = min(n_idx / p.ag.rows_per_slab, p.ag.world - 1);
+                        const int s_hi = min(last_row / p.ag.rows_per_slab, p.ag.world - 1);
+                        for (int sl = s_lo; sl <= s_hi; ++sl) {
+                            uint32_t spins = 0;
+                            while (ld_acquire_gpu(p.ag.flags + sl) < static_cast<uint32_t>(ag_chunks_per_slab)) {
+                                if (++spins > (1u << 26)) {
+                                    printf("[b200] AG-fused GEMM: slab %d never arrived (block %d)\n", sl, blockIdx.x);
+                                    __trap();
+                                }
+                            }
+                        }
+                        fence_proxy_async_all();  // generic-proxy peer copies -> async-proxy (TMA) reads
+                    }
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     const int k_idx = kb * kBlockK;
@@ -238,6 +282,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
                     const uint32_t prev = iter - 2;
                     mbar_wait(&tmem_empty_bar[prev & 1], (prev >> 1) & 1);
                 }
+            }
+        }
+    } else if (warp_idx == 3) {
+        // ================================= All-gather copier (AG fusion only) =================================
+        if (p.ag.world > 1) {
+            const int total_chunks = p.ag.world * ag_chunks_per_slab;
+            for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+                const int k = c / ag_chunks_per_slab;            // arrival index: 0 = own slab
+                const int sl = (p.ag.rank + k) % p.ag.world;      // slab pulled now (ranks start at different peers)
+                const int64_t off = static_cast<int64_t>(c - k * ag_chunks_per_slab) * kAgChunkBytes;
+                const int64_t nbytes = min(static_cast<int64_t>(kAgChunkBytes), p.ag.slab_bytes - off);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.ag.peer_src[sl]) + off;
+                uint8_t* dst = static_cast<uint8_t*>(p.ag.dst) + static_cast<int64_t>(sl) * p.ag.slab_bytes + off;
+                const int nvec = static_cast<int>(nbytes / 16);
+                int i = lane;
+                for (; i + 7 * 32 < nvec; i += 8 * 32) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = ld_peer_v4(src + static_cast<int64_t>(i + u * 32) * 16);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(i + u * 32) * 16) = v[u];
+                }
+                for (; i < nvec; i += 32) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(i) * 16) = ld_peer_v4(src + static_cast<int64_t>(i) * 16);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) red_release_gpu_add(p.ag.flags + sl, 1);
             }
         }
     } else if (warp_idx >= 4) {
@@ -499,7 +569,7 @@ int num_sms() {
 
 template <int kMajorA, int kMajorB, int BLOCK_N, int kStages>
 void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, const GemmOperand* aux, int M, int N,
-            int K, const GemmEpilogue& epi, int max_ctas, cudaStream_t stream) {
+            int K, const GemmEpilogue& epi, int max_ctas, cudaStream_t stream, const GemmAgFuse* ag) {
     constexpr int LOAD_N = BLOCK_N / 2;
     constexpr int kSmem = kCdBufs * kCdBufBytes + kStages * (kBlockM * kBlockK * 2 + LOAD_N * kBlockK * 2) +
                           (2 * kStages + 4) * 8 + 16;
@@ -524,6 +594,15 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
     p.m_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
     p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
     p.epi = epi;
+    p.n_rot = 0;
+    if (ag != nullptr && ag->world > 1) {
+        if (kMajorB != 0 || p.batch != 1) throw std::runtime_error("gemm: AG fusion needs a K-major, un-batched B");
+        if (static_cast<int64_t>(ag->rows_per_slab) * K * 2 != ag->slab_bytes || ag->slab_bytes % 16 != 0)
+            throw std::runtime_error("gemm: AG fusion needs whole rows per slab");
+        p.ag = *ag;
+        p.n_rot = static_cast<int>((static_cast<int64_t>(ag->rank) * ag->rows_per_slab) / BLOCK_N) % p.n_tiles;
+        cudaMemsetAsync(ag->flags, 0, sizeof(uint32_t) * ag->world, stream);
+    }
     const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.batch;
     int sms = num_sms();
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
@@ -551,7 +630,7 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
 
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
-               cudaStream_t stream) {
+               cudaStream_t stream, const GemmAgFuse* ag) {
     if (N % 8 != 0 && (epi.residual || epi.aux_in))
         throw std::runtime_error("gemm: N must be a multiple of 8 when residual/aux_in are used");
     if (epi.act == kActDGelu && (epi.residual != nullptr || epi.aux_in == nullptr))
@@ -561,7 +640,7 @@ void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int majo
     if (block_n == 0) block_n = (N > 128) ? 256 : 128;
 #define B200_DISPATCH(MA, MB, BN, ST)                                                             \
     if (major_a == MA && major_b == MB && block_n == BN) {                                        \
-        launch<MA, MB, BN, ST>(A, B, D, aux_out, M, N, K, epi, max_ctas, stream);                 \
+        launch<MA, MB, BN, ST>(A, B, D, aux_out, M, N, K, epi, max_ctas, stream, ag);             \
         return;                                                                                   \
     }
     B200_DISPATCH(0, 0, 256, 5)

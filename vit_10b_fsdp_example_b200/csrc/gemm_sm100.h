@@ -30,10 +30,25 @@ struct GemmEpilogue {
     int has_aux_out = 0;  // also store the pre-activation (after bias) through the aux tensor map
 };
 
+// All-gather fused into the GEMM (B operand = an FSDP-sharded weight, rank r owns rows [r*rows_per_slab, ...)):
+// warp 3 of every CTA pulls the peers' slabs over NVLink (P2P loads from symmetric memory) straight into the
+// local gathered buffer and bumps a per-slab counter; the TMA producer waits for the slab(s) a tile needs, and tiles
+// are visited in slab-arrival order (own slab first), so the tensor cores start after 1/W of the weight is there
+// and the transfer of the rest hides under the math.  No NCCL, no host sync, no separate gather kernel.
+struct GemmAgFuse {
+    int world = 0;            // 0/1 = disabled
+    int rank = 0;
+    int rows_per_slab = 0;    // B rows (output features) owned by each rank
+    int64_t slab_bytes = 0;   // bytes per slab
+    uint64_t peer_src[16] = {0};  // per rank: address of its slab (peer-mapped symmetric memory)
+    void* dst = nullptr;      // local gathered B (slab r lands at dst + r * slab_bytes)
+    uint32_t* flags = nullptr;  // [world] device counters; zeroed by gemm_bf16 before the launch
+};
+
 // D[b][M, N] = epi(A[b] (M x K) * B[b] (N x K)^T).  major_x: 0 = K contiguous, 1 = M/N contiguous.
 // block_n: 0 = auto, else 128 / 256.  max_ctas: 0 = all SMs (used to carve SMs out for comm kernels).
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
-               cudaStream_t stream);
+               cudaStream_t stream, const GemmAgFuse* ag = nullptr);
 
 }  // namespace b200

@@ -132,8 +132,9 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[
     pa, pm = cfg.att_dropout, cfg.mlp_dropout
     use_drop = drop is not None and drop.training and (pa > 0 or pm > 0)
     site = block_idx * 8
+    ag = getattr(p, "ag", None) or {}  # weights whose all-gather is fused into the GEMM that consumes them
     h1, m1, r1 = ops.ln_fwd(x, p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)
-    qkv = ops.linear_fwd(h1, p["attn.qkv.weight"], p["attn.qkv.bias"])
+    qkv = ops.linear_fwd(h1, p["attn.qkv.weight"], p["attn.qkv.bias"], ag=ag.get("attn.qkv.weight"))
     masks = {}
     if use_drop and pa > 0:
         masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
@@ -149,9 +150,10 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[
         x1 = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"], residual=x)
     h2, m2, r2 = ops.ln_fwd(x1, p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)
     if save:
-        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", want_preact=True)
+        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", want_preact=True,
+                              ag=ag.get("mlp.fc1.weight"))
     else:
-        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu"), None
+        g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", ag=ag.get("mlp.fc1.weight")), None
     if use_drop and pm > 0:
         masks["fc1"] = drop.mask(g.shape, pm, site + 2, x.device)
         masks["fc2"] = drop.mask(x.shape, pm, site + 3, x.device)

@@ -91,10 +91,10 @@ def _bias_ok(b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 def gemm_raw(a, lda, major_a, b, ldb, major_b, d, ldd, M, N, K, *, bias=None, residual=None, ld_res=0,
              res_row_mod=0, aux_in=None, ld_aux=0, aux_out=None, ld_aux_out=0, colsum=None, colsum_bi_stride=0,
-             act=ACT_NONE, batch=(), block_n=0, max_ctas=None):
+             act=ACT_NONE, batch=(), block_n=0, max_ctas=None, ag=()):
     _C.gemm(a, lda, major_a, b, ldb, major_b, d, ldd, M, N, K, bias, residual, ld_res, res_row_mod, aux_in, ld_aux,
             aux_out, ld_aux_out, colsum, colsum_bi_stride, act, list(batch), block_n,
-            _max_ctas if max_ctas is None else max_ctas)
+            _max_ctas if max_ctas is None else max_ctas, list(ag))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,7 +121,9 @@ def ln_bwd(dy, x, w, mean, rstd, dres=None, want_dxsum: bool = False):
 # Linear
 # ------------------------------------------------------------------------------------------------
 def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_row_mod: int = 0,
-               want_preact: bool = False):
+               want_preact: bool = False, ag=None):
+    """ag: optional all-gather fusion spec (see Sm100Backend.ag_fuse_spec): the kernel itself pulls the peers'
+    shards of `w` over NVLink while it computes."""
     M, K = x.shape
     N = w.shape[0]
     x, w = _tma_rows(x), _tma_rows(w)
@@ -130,7 +132,7 @@ def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_ro
     pre = torch.empty(M, ldy, dtype=x.dtype, device=x.device) if want_preact else None
     gemm_raw(x, _ld(x), 0, w, _ld(w), 0, y, ldy, M, N, K, bias=_bias_ok(bias), residual=residual,
              ld_res=_ld(residual) if residual is not None else 0, res_row_mod=res_row_mod, aux_out=pre,
-             ld_aux_out=ldy, act=ACT_GELU if act == "gelu" else ACT_NONE)
+             ld_aux_out=ldy, act=ACT_GELU if act == "gelu" else ACT_NONE, ag=ag or ())
     if ldy != N:
         y = y[:, :N].contiguous()
         pre = pre[:, :N].contiguous() if pre is not None else None

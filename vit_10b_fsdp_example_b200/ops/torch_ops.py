@@ -65,7 +65,7 @@ def dgelu(u):
 
 
 def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_row_mod: int = 0,
-               want_preact: bool = False):
+               want_preact: bool = False, ag=None):
     """y = act(x @ w.T + bias) + residual.  residual rows may be broadcast with period res_row_mod."""
     y = _f32(x) @ _f32(w).t()
     if bias is not None:

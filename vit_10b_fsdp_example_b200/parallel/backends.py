@@ -37,7 +37,10 @@ class TorchDistBackend:
         return torch.zeros(numel, dtype=dtype, device=self.device)
 
     # ---- collectives ----
-    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor) -> None:
+    def fusable_params(self, layout: UnitLayout):
+        return ()
+
+    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor, exclude=()) -> None:
         if self.world == 1:
             if out_full.data_ptr() != shard.data_ptr():
                 out_full[: shard.numel()].copy_(shard)
@@ -172,16 +175,51 @@ class Sm100Backend(TorchDistBackend):
         self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, self._next_seq(slot))
 
     # ---- segment tables (device int64), built once per (layout, purpose) ----
-    def _ag_table(self, layout: UnitLayout, esize: int):
-        key = ("ag", id(layout), esize)
+    def _ag_table(self, layout: UnitLayout, esize: int, exclude=()):
+        key = ("ag", id(layout), esize, tuple(sorted(exclude)))
         if key not in self._seg_cache:
             chunk = self._C.ag_chunk_bytes()
             rows, prefix = [], 0
-            for (r, soff, doff, n) in layout.gather_segments():
-                rows.append([r, soff * esize, doff * esize, n * esize, prefix])
-                prefix += -(-n * esize // chunk)
+            for g in layout.groups:
+                if g.name in exclude:
+                    continue  # gathered by the GEMM that consumes it (AG fusion)
+                for r in range(self.world):
+                    n = g.shard_len
+                    rows.append([r, g.shard_offset * esize, (g.full_offset + r * n) * esize, n * esize, prefix])
+                    prefix += -(-n * esize // chunk)
             self._seg_cache[key] = (torch.tensor(rows, dtype=torch.int64, device=self.device), prefix)
         return self._seg_cache[key]
+
+    # ---- all-gather fused into the consuming GEMM ----
+    FUSED_PARAMS = ("attn.qkv.weight", "mlp.fc1.weight")
+
+    def fusable_params(self, layout: UnitLayout):
+        """Weights whose all-gather can run inside the forward GEMM that consumes them: per-parameter shard
+        groups made of whole rows (dim-0 slabs), no padding."""
+        if self.world == 1 or layout.flatten:
+            return ()
+        ok = []
+        for g in layout.groups:
+            if g.name not in self.FUSED_PARAMS:
+                continue
+            spec = next(p for p in layout.params if p.name == g.name)
+            rows, cols = spec.shape
+            if rows % self.world == 0 and g.shard_len == (rows // self.world) * cols and (g.shard_len * 2) % 16 == 0:
+                ok.append(g.name)
+        return tuple(ok)
+
+    def ag_fuse_spec(self, layout: UnitLayout, shard: torch.Tensor, full_buf: torch.Tensor, name: str):
+        """Argument list for `_C.gemm(..., ag=...)`: the kernel pulls every rank's slab of `name` itself."""
+        g = next(x for x in layout.groups if x.name == name)
+        spec = next(p for p in layout.params if p.name == name)
+        esize = shard.element_size()
+        key = ("flags", full_buf.data_ptr(), name)
+        if key not in self._seg_cache:
+            self._seg_cache[key] = torch.zeros(16, dtype=torch.int32, device=self.device)
+        flags = self._seg_cache[key]
+        peers = [p + g.shard_offset * esize for p in self._peer[shard.data_ptr()]]
+        return [self.world, self.rank, spec.shape[0] // self.world, g.shard_len * esize,
+                full_buf.data_ptr() + g.full_offset * esize, flags.data_ptr()] + peers
 
     def _rs_table(self, layout: UnitLayout, esize: int):
         key = ("rs", id(layout), esize)
@@ -195,10 +233,10 @@ class Sm100Backend(TorchDistBackend):
         return self._seg_cache[key]
 
     # ---- collectives ----
-    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor) -> None:
+    def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor, exclude=()) -> None:
         if self.world == 1:
             return super().all_gather(layout, shard, out_full)
-        table, chunks = self._ag_table(layout, shard.element_size())
+        table, chunks = self._ag_table(layout, shard.element_size(), exclude)
         self._C.p2p_all_gather(self._peer[shard.data_ptr()], self.rank, out_full, table, chunks, self.comm_ctas)
 
     def reduce_scatter(self, layout: UnitLayout, full_grad: torch.Tensor, out_shard: torch.Tensor,

@@ -58,6 +58,7 @@ class FsdpUnit:
         self.full_grad: Optional[torch.Tensor] = None
         self.gather_event = None
         self.reduce_event = None
+        self.fused_pending = ()  # weights the next block_forward has to gather itself (AG-fused GEMMs)
 
     @property
     def compute_shard(self) -> torch.Tensor:
@@ -70,7 +71,7 @@ class FSDPViT:
     def __init__(self, vcfg: ViTConfig, *, world: int = 1, rank: int = 0, device=None, dtype=torch.float32,
                  reshard_after_forward: bool = True, flatten_parameters: bool = False, grad_ckpt: bool = True,
                  run_without_fsdp: bool = False, shard_on_cpu: bool = False, backend: str = "torchdist",
-                 seed: int = 0, init_device: str = "cpu", verbose_build=None):
+                 seed: int = 0, init_device: str = "cpu", verbose_build=None, fuse_all_gather: bool = True):
         self.cfg = vcfg
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.dtype = dtype
@@ -102,6 +103,7 @@ class FSDPViT:
         self._sumsq = None
         self._fused_sumsq = False
         self.step_count = 0
+        self.fuse_all_gather = fuse_all_gather
 
         # ---- streams ----
         if self.is_cuda:
@@ -222,10 +224,16 @@ class FSDPViT:
     def _param_buf_index(self, unit: FsdpUnit) -> int:
         return unit.index % len(self._param_bufs)
 
-    def _issue_gather(self, unit: FsdpUnit) -> None:
-        """Enqueue the unit's all-gather on the comm stream (prefetch).  No-op if already resident."""
+    def _issue_gather(self, unit: FsdpUnit, fuse: bool = False) -> None:
+        """Enqueue the unit's all-gather on the comm stream (prefetch).  No-op if already resident.
+
+        fuse=True: the next thing that runs on this unit is a block_forward, so the big weights consumed by
+        its qkv / fc1 GEMMs are left out here and pulled by those GEMM kernels themselves (AG fusion)."""
         if self._alias or unit.gather_event is not None:
             return
+        exclude = ()
+        if fuse and self.fuse_all_gather and unit is not self.root:
+            exclude = self.backend.fusable_params(unit.layout)
         if unit is self.root:
             buf = unit.full
             free_ev = None
@@ -235,9 +243,19 @@ class FSDPViT:
             free_ev = self._param_buf_free[bi]
         with self._on_comm():
             self._wait(free_ev)
-            self.backend.all_gather(unit.layout, unit.compute_shard, buf)
+            self.backend.all_gather(unit.layout, unit.compute_shard, buf, exclude)
             unit.gather_event = self._record(self._new_event())
         unit.full = buf
+        unit.fused_pending = exclude
+
+    def _views(self, unit: FsdpUnit):
+        """Parameter views of a resident unit; hands pending AG-fusion specs to the first block_forward."""
+        p = unit.layout.param_views(unit.full)
+        if unit.fused_pending:
+            p.ag = {n: self.backend.ag_fuse_spec(unit.layout, unit.compute_shard, unit.full, n)
+                    for n in unit.fused_pending}
+            unit.fused_pending = ()
+        return p
 
     def _wait_gather(self, unit: FsdpUnit) -> None:
         if not self._alias:
@@ -306,7 +324,7 @@ class FSDPViT:
         # -------- forward --------
         self._issue_gather(self.root)
         if blocks:
-            self._issue_gather(blocks[0])
+            self._issue_gather(blocks[0], fuse=True)
         self._wait_gather(self.root)
         rp = self.root.layout.param_views(self.root.full)
         x, stem_saved = vit.stem_forward(ops, cfg, rp, images, self.dtype, self.drop)
@@ -314,9 +332,9 @@ class FSDPViT:
         saved_all = []
         for i, u in enumerate(blocks):
             if i + 1 < len(blocks):
-                self._issue_gather(blocks[i + 1])
+                self._issue_gather(blocks[i + 1], fuse=True)
             self._wait_gather(u)
-            p = u.layout.param_views(u.full)
+            p = self._views(u)
             if self.grad_ckpt:
                 ckpt.append(x)
                 x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
@@ -333,11 +351,11 @@ class FSDPViT:
         del head_saved, logits, dlogits
         for i in range(len(blocks) - 1, -1, -1):
             u = blocks[i]
-            self._issue_gather(u)
+            self._issue_gather(u, fuse=self.grad_ckpt)
             if i - 1 >= 0:
-                self._issue_gather(blocks[i - 1])  # prefetch the next block of the backward sweep
+                self._issue_gather(blocks[i - 1], fuse=self.grad_ckpt)  # prefetch for the backward sweep
             self._wait_gather(u)
-            p = u.layout.param_views(u.full)
+            p = self._views(u)
             if self.grad_ckpt:
                 xin = ckpt.pop()
                 _, s = vit.block_forward(ops, cfg, p, xin, B, save=True, drop=self.drop, block_idx=i)
@@ -368,16 +386,16 @@ class FSDPViT:
         blocks = self.units
         self._issue_gather(self.root)
         if blocks:
-            self._issue_gather(blocks[0])
+            self._issue_gather(blocks[0], fuse=True)
         self._wait_gather(self.root)
         rp = self.root.layout.param_views(self.root.full)
         drop = self.drop if self.training else None
         x, _ = vit.stem_forward(ops, cfg, rp, images, self.dtype, drop)
         for i, u in enumerate(blocks):
             if i + 1 < len(blocks):
-                self._issue_gather(blocks[i + 1])
+                self._issue_gather(blocks[i + 1], fuse=True)
             self._wait_gather(u)
-            x, _ = vit.block_forward(ops, cfg, u.layout.param_views(u.full), x, B, save=False, drop=drop, block_idx=i)
+            x, _ = vit.block_forward(ops, cfg, self._views(u), x, B, save=False, drop=drop, block_idx=i)
             self._release_params(u)
         logits, _ = vit.head_forward(ops, cfg, rp, x, B)
         self.root.gather_event = None

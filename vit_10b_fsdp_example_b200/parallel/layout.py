@@ -33,6 +33,17 @@ def round_up(a: int, b: int) -> int:
     return ceil_div(a, b) * b
 
 
+class ParamViews(dict):
+    """name -> parameter view.  ``ag`` optionally maps a weight name to an all-gather-fusion spec: the forward GEMM
+    that consumes that weight also pulls its shards from the peers (see Sm100Backend.ag_fuse_spec)."""
+
+    ag: dict = {}
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.ag = {}
+
+
 @dataclass
 class ParamSpec:
     name: str
@@ -96,9 +107,9 @@ class UnitLayout:
     def payload_numel(self) -> int:
         return sum(p.numel for p in self.params)
 
-    def param_views(self, full_buf) -> Dict[str, "object"]:
+    def param_views(self, full_buf) -> "ParamViews":
         """Name -> shaped view into a full buffer (torch tensor of >= full_numel elements)."""
-        return {p.name: full_buf[p.full_offset: p.full_offset + p.numel].view(p.shape) for p in self.params}
+        return ParamViews({p.name: full_buf[p.full_offset: p.full_offset + p.numel].view(p.shape) for p in self.params})
 
     def gather_segments(self) -> List[Tuple[int, int, int, int]]:
         """(src_rank, src_shard_offset, dst_full_offset, length) in elements, for every rank."""
