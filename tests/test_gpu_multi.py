@@ -124,7 +124,7 @@ def _collectives_worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def _train_worker(rank, world, port, backend, out_path, flatten, reshard):
+def _train_worker(rank, world, port, backend, out_path, flatten, reshard, clip=1.0, fuse_opt=False):
     dist = _init(rank, world, port)
     from vit_10b_fsdp_example_b200.config import ViTConfig
     from vit_10b_fsdp_example_b200.parallel import FSDPViT, ShardedAdamW
@@ -134,7 +134,8 @@ def _train_worker(rank, world, port, backend, out_path, flatten, reshard):
                     num_classes=96)
     model = FSDPViT(cfg, world=world, rank=rank, device=dev, dtype=torch.bfloat16, backend=backend, seed=1,
                     flatten_parameters=flatten, reshard_after_forward=reshard)
-    opt = ShardedAdamW(model, lr=1e-3, weight_decay=0.1)
+    opt = ShardedAdamW(model, lr=1e-3, weight_decay=0.1, fuse_into_reduce_scatter=fuse_opt)
+    assert opt.fused == (fuse_opt and backend == "sm100")
     g = torch.Generator().manual_seed(0)
     images = torch.randn(8, 3, 112, 112, generator=g)
     target = torch.randint(0, 96, (8,), generator=g)
@@ -142,7 +143,7 @@ def _train_worker(rank, world, port, backend, out_path, flatten, reshard):
     losses, norms = [], []
     for _ in range(6):
         loss = model.forward_backward(images[rank * lb:(rank + 1) * lb].to(dev), target[rank * lb:(rank + 1) * lb].to(dev))
-        norm = model.clip_grad_norm_(1.0)
+        norm = model.clip_grad_norm_(clip) if clip > 0 else torch.zeros(1)
         opt.step()
         lv = loss.detach().float().reshape(1).clone()
         dist.all_reduce(lv)
@@ -188,4 +189,20 @@ def test_sm100_backend_matches_nccl_backend(flatten, reshard, tmp_path):
         assert abs(x - y) < 0.03 * abs(x) + 0.02, (a, b)
     for x, y in zip(a["norms"], b["norms"]):
         assert abs(x - y) < 0.05 * abs(x) + 0.02, (a, b)
+    assert b["losses"][-1] < b["losses"][0]
+
+
+def test_adamw_fused_into_reduce_scatter(tmp_path):
+    """Clipping off: the AdamW update runs inside each unit's reduce-scatter kernel during backward and must give
+    the same trajectory as the separate optimizer step on the NCCL backend."""
+    world = 2
+    _need_gpus(world)
+    outs = {}
+    for name, backend, fuse in (("ref", "torchdist", False), ("fused", "sm100", True)):
+        out = str(tmp_path / f"{name}.json")
+        _spawn(_train_worker, world, (backend, out, False, True, 0.0, fuse))
+        outs[name] = json.load(open(out))
+    a, b = outs["ref"], outs["fused"]
+    for x, y in zip(a["losses"], b["losses"]):
+        assert abs(x - y) < 0.03 * abs(x) + 0.02, (a, b)
     assert b["losses"][-1] < b["losses"][0]

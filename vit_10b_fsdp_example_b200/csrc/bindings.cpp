@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cmath>
 #include <optional>
 #include <vector>
 
@@ -176,19 +177,42 @@ void p2p_all_gather(std::vector<int64_t> peer_ptrs, int64_t rank, Tensor out, Te
     b200::p2p_all_gather(peer_ptrs, (int)rank, out.data_ptr(), seg_ptr(seg_table), (int)seg_table.size(0),
                          total_chunks, (int)max_ctas, cur_stream());
 }
+// adam = [] or (hi, lo, m, v tensors given separately) + hyper = [lr, beta1, beta2, eps, wd, step]
+bool make_adam(const OptT& hi, const OptT& lo, const OptT& m, const OptT& v, const std::vector<double>& hyper,
+               b200::AdamFuse& a) {
+    if (!hi.has_value()) return false;
+    TORCH_CHECK(lo.has_value() && m.has_value() && v.has_value() && hyper.size() == 6, "bad fused-AdamW arguments");
+    TORCH_CHECK(hi->scalar_type() == at::kBFloat16 && lo->scalar_type() == at::kShort, "hi: bf16, lo: int16");
+    a.hi = reinterpret_cast<uint16_t*>(hi->data_ptr());
+    a.lo = reinterpret_cast<int16_t*>(lo->data_ptr());
+    a.m = f32_ptr(*m);
+    a.v = f32_ptr(*v);
+    a.lr = (float)hyper[0], a.beta1 = (float)hyper[1], a.beta2 = (float)hyper[2], a.eps = (float)hyper[3];
+    a.wd = (float)hyper[4];
+    a.inv_bc1 = 1.f / (1.f - powf(a.beta1, (float)hyper[5]));
+    a.inv_bc2 = 1.f / (1.f - powf(a.beta2, (float)hyper[5]));
+    return true;
+}
 void p2p_reduce_scatter(std::vector<int64_t> peer_ptrs, int64_t rank, Tensor out, Tensor seg_table,
-                        int64_t total_chunks, bool in_is_bf16, double scale, OptT sumsq_out, int64_t max_ctas) {
+                        int64_t total_chunks, bool in_is_bf16, double scale, OptT sumsq_out, int64_t max_ctas, OptT hi,
+                        OptT lo, OptT m, OptT v, std::vector<double> hyper) {
     c10::cuda::CUDAGuard guard(out.device());
+    b200::AdamFuse a;
+    const bool fused = make_adam(hi, lo, m, v, hyper, a);
     b200::p2p_reduce_scatter(peer_ptrs, (int)rank, f32_ptr(out), seg_ptr(seg_table), (int)seg_table.size(0),
                              total_chunks, in_is_bf16, (float)scale,
-                             sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr, (int)max_ctas, cur_stream());
+                             sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr, (int)max_ctas, cur_stream(),
+                             fused ? &a : nullptr);
 }
 void nvls_reduce_scatter(int64_t mc_ptr, int64_t rank, int64_t world, Tensor out, Tensor seg_table,
-                         int64_t total_chunks, double scale, OptT sumsq_out, int64_t max_ctas) {
+                         int64_t total_chunks, double scale, OptT sumsq_out, int64_t max_ctas, OptT hi, OptT lo, OptT m,
+                         OptT v, std::vector<double> hyper) {
     c10::cuda::CUDAGuard guard(out.device());
+    b200::AdamFuse a;
+    const bool fused = make_adam(hi, lo, m, v, hyper, a);
     b200::nvls_reduce_scatter(mc_ptr, (int)rank, (int)world, f32_ptr(out), seg_ptr(seg_table), (int)seg_table.size(0),
                               total_chunks, (float)scale, sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr,
-                              (int)max_ctas, cur_stream());
+                              (int)max_ctas, cur_stream(), fused ? &a : nullptr);
 }
 void signal_barrier(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, int64_t slot, int64_t seq) {
     b200::signal_barrier(flag_ptrs, (int)rank, (int)world, (int)slot, (uint32_t)seq, cur_stream());

@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(kCommThreads) p2p_all_gather_kernel(PeerPtrs p
 }
 
 // seg_table row (reduce-scatter): [full_off_bytes, shard_off_elems, nelems, chunk_prefix]
-template <bool kBf16In, bool kNvls>
+template <bool kBf16In, bool kNvls, bool kAdam>
 __global__ void __launch_bounds__(kCommThreads) reduce_scatter_kernel(PeerPtrs peers, uint64_t mc_base, int rank,
                                                                       int world, float* __restrict__ out,
                                                                       const int64_t* __restrict__ seg, int nseg,
                                                                       int64_t total_chunks, float scale,
-                                                                      float* __restrict__ sumsq_out) {
+                                                                      float* __restrict__ sumsq_out, AdamFuse adam) {
     __shared__ float red[kCommThreads / 32];
     float sq = 0.f;
     int s = 0;
@@ -172,9 +172,29 @@ __global__ void __launch_bounds__(kCommThreads) reduce_scatter_kernel(PeerPtrs p
                 acc[q] *= scale;
                 sq += acc[q] * acc[q];
             }
-            float4* d4 = reinterpret_cast<float4*>(dst + i * kVec);
-            d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            if constexpr (kVec == 8) d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if constexpr (kAdam) {
+                // Sharded AdamW right here: the reduced gradient never goes to memory.
+                const int64_t e = row[1] + e0 + i * kVec;  // element offset inside the shard
+                const float decay = 1.f - adam.lr * adam.wd;
+#pragma unroll
+                for (int q = 0; q < kVec; ++q) {
+                    const int32_t bits = (static_cast<int32_t>(adam.hi[e + q]) << 16) + static_cast<int32_t>(adam.lo[e + q]);
+                    float w = __int_as_float(bits);
+                    const float mi = adam.beta1 * adam.m[e + q] + (1.f - adam.beta1) * acc[q];
+                    const float vi = adam.beta2 * adam.v[e + q] + (1.f - adam.beta2) * acc[q] * acc[q];
+                    adam.m[e + q] = mi;
+                    adam.v[e + q] = vi;
+                    w = w * decay - adam.lr * (mi * adam.inv_bc1) / (sqrtf(vi * adam.inv_bc2) + adam.eps);
+                    const int32_t nb = __float_as_int(w);
+                    const int32_t h = (nb + 0x8000) >> 16;
+                    adam.hi[e + q] = static_cast<uint16_t>(h & 0xFFFF);
+                    adam.lo[e + q] = static_cast<int16_t>(nb - (h << 16));
+                }
+            } else {
+                float4* d4 = reinterpret_cast<float4*>(dst + i * kVec);
+                d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                if constexpr (kVec == 8) d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
         }
     }
     if (sumsq_out != nullptr) {
@@ -270,26 +290,38 @@ void p2p_all_gather(const std::vector<int64_t>& peer_ptrs, int rank, void* out, 
 
 void p2p_reduce_scatter(const std::vector<int64_t>& peer_ptrs, int rank, float* out, const int64_t* seg_table_dev,
                         int nseg, int64_t total_chunks, bool in_is_bf16, float scale, float* sumsq_out, int max_ctas,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const AdamFuse* adam) {
     if (total_chunks == 0) return;
     const int world = static_cast<int>(peer_ptrs.size());
     const int grid = static_cast<int>(std::min<int64_t>(total_chunks, max_ctas > 0 ? max_ctas : 32));
-    if (in_is_bf16)
-        reduce_scatter_kernel<true, false><<<grid, kCommThreads, 0, stream>>>(
-            to_peers(peer_ptrs), 0, rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out);
+    const AdamFuse a = adam != nullptr ? *adam : AdamFuse{};
+    if (in_is_bf16 && adam != nullptr)
+        reduce_scatter_kernel<true, false, true><<<grid, kCommThreads, 0, stream>>>(
+            to_peers(peer_ptrs), 0, rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out, a);
+    else if (in_is_bf16)
+        reduce_scatter_kernel<true, false, false><<<grid, kCommThreads, 0, stream>>>(
+            to_peers(peer_ptrs), 0, rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out, a);
+    else if (adam != nullptr)
+        throw std::runtime_error("reduce_scatter: fused AdamW needs bf16 gradients");
     else
-        reduce_scatter_kernel<false, false><<<grid, kCommThreads, 0, stream>>>(
-            to_peers(peer_ptrs), 0, rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out);
+        reduce_scatter_kernel<false, false, false><<<grid, kCommThreads, 0, stream>>>(
+            to_peers(peer_ptrs), 0, rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out, a);
     check_launch("p2p_reduce_scatter");
 }
 
 void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const int64_t* seg_table_dev, int nseg,
-                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream) {
+                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream,
+                         const AdamFuse* adam) {
     if (total_chunks == 0) return;
     const int grid = static_cast<int>(std::min<int64_t>(total_chunks, max_ctas > 0 ? max_ctas : 32));
     PeerPtrs none{};
-    reduce_scatter_kernel<true, true><<<grid, kCommThreads, 0, stream>>>(
-        none, static_cast<uint64_t>(mc_ptr), rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out);
+    const AdamFuse a = adam != nullptr ? *adam : AdamFuse{};
+    if (adam != nullptr)
+        reduce_scatter_kernel<true, true, true><<<grid, kCommThreads, 0, stream>>>(
+            none, static_cast<uint64_t>(mc_ptr), rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out, a);
+    else
+        reduce_scatter_kernel<true, true, false><<<grid, kCommThreads, 0, stream>>>(
+            none, static_cast<uint64_t>(mc_ptr), rank, world, out, seg_table_dev, nseg, total_chunks, scale, sumsq_out, a);
     check_launch("nvls_reduce_scatter");
 }
 

@@ -11,11 +11,21 @@ namespace b200 {
 //   reduce-scatter : [full_off_bytes, shard_off_elems, nelems, chunk_prefix]          (chunk = rs_chunk_elems())
 void p2p_all_gather(const std::vector<int64_t>& peer_ptrs, int rank, void* out, const int64_t* seg_table_dev,
                     int nseg, int64_t total_chunks, int max_ctas, cudaStream_t stream);
+// Optional AdamW fused into the reduce-scatter epilogue (only legal when gradient clipping is off: the update
+// of a shard then needs nothing but its own reduced gradient).  `out` is not written in that case.
+struct AdamFuse {
+    uint16_t* hi = nullptr;  // split-fp32 master shard (see elementwise.cu)
+    int16_t* lo = nullptr;
+    float* m = nullptr;
+    float* v = nullptr;
+    float lr = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, wd = 0.f, inv_bc1 = 1.f, inv_bc2 = 1.f;
+};
 void p2p_reduce_scatter(const std::vector<int64_t>& peer_ptrs, int rank, float* out, const int64_t* seg_table_dev,
                         int nseg, int64_t total_chunks, bool in_is_bf16, float scale, float* sumsq_out, int max_ctas,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const AdamFuse* adam = nullptr);
 void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const int64_t* seg_table_dev, int nseg,
-                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream);
+                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream,
+                         const AdamFuse* adam = nullptr);
 // flags: uint32 [slot][16] per rank; scratch: float [slot][16][16] per rank (both in symmetric memory)
 void signal_barrier(const std::vector<int64_t>& flag_ptrs, int rank, int world, int slot, uint32_t seq,
                     cudaStream_t stream);

@@ -24,6 +24,7 @@ from .layout import UnitLayout
 
 class TorchDistBackend:
     name = "torchdist"
+    supports_fused_adam = False
 
     def __init__(self, world: int, rank: int, device: torch.device):
         self.world, self.rank, self.device = world, rank, device
@@ -239,19 +240,24 @@ class Sm100Backend(TorchDistBackend):
         table, chunks = self._ag_table(layout, shard.element_size(), exclude)
         self._C.p2p_all_gather(self._peer[shard.data_ptr()], self.rank, out_full, table, chunks, self.comm_ctas)
 
+    supports_fused_adam = True
+
     def reduce_scatter(self, layout: UnitLayout, full_grad: torch.Tensor, out_shard: torch.Tensor,
-                       sumsq: Optional[torch.Tensor] = None, ops=None) -> None:
+                       sumsq: Optional[torch.Tensor] = None, ops=None, adam=None) -> None:
+        """adam = (hi, lo, m, v, [lr, beta1, beta2, eps, wd, step]) fuses the sharded AdamW update into the kernel
+        (legal only without gradient clipping); out_shard is then left untouched."""
         if self.world == 1:
             return super().reduce_scatter(layout, full_grad, out_shard, sumsq, ops)
         table, chunks = self._rs_table(layout, full_grad.element_size())
         scale = 1.0 / self.world
+        a = tuple(adam) if adam is not None else (None, None, None, None, [])
         self.device_barrier(slot=1)  # every rank's gradients for this unit are complete
         if self.use_nvls and full_grad.dtype == torch.bfloat16:
             self._C.nvls_reduce_scatter(self._mc[full_grad.data_ptr()], self.rank, self.world, out_shard, table,
-                                        chunks, scale, sumsq, self.comm_ctas)
+                                        chunks, scale, sumsq, self.comm_ctas, *a)
         else:
             self._C.p2p_reduce_scatter(self._peer[full_grad.data_ptr()], self.rank, out_shard, table, chunks,
-                                       full_grad.dtype == torch.bfloat16, scale, sumsq, self.comm_ctas)
+                                       full_grad.dtype == torch.bfloat16, scale, sumsq, self.comm_ctas, *a)
         self.device_barrier(slot=2)  # every rank is done reading: the buffer may be overwritten
 
     def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:

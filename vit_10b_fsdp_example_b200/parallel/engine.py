@@ -104,6 +104,7 @@ class FSDPViT:
         self._fused_sumsq = False
         self.step_count = 0
         self.fuse_all_gather = fuse_all_gather
+        self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
 
         # ---- streams ----
         if self.is_cuda:
@@ -291,10 +292,15 @@ class FSDPViT:
         if self._alias:
             return
         ready = self._record(self._new_event())
+        adam = self._fused_opt.fused_args(unit) if self._fused_opt is not None else None
         with self._on_comm():
             self._wait(ready)
-            self.backend.reduce_scatter(unit.layout, unit.full_grad, unit.shard_grad,
-                                        self._sumsq if self._fused_sumsq else None, self.ops)
+            if adam is not None:
+                self.backend.reduce_scatter(unit.layout, unit.full_grad, unit.shard_grad,
+                                            self._sumsq if self._fused_sumsq else None, self.ops, adam=adam)
+            else:
+                self.backend.reduce_scatter(unit.layout, unit.full_grad, unit.shard_grad,
+                                            self._sumsq if self._fused_sumsq else None, self.ops)
             ev = self._record(self._new_event())
         unit.reduce_event = ev
         if unit is not self.root:
@@ -408,6 +414,9 @@ class FSDPViT:
         """Computes the global gradient norm and arms the clip coefficient consumed by the next
         ``optimizer.step()`` (the scaling is fused into the AdamW kernel instead of a separate pass)."""
         ops = self.ops
+        if self._fused_opt is not None:
+            raise RuntimeError("clip_grad_norm_ cannot be used with AdamW fused into the reduce-scatter: the update "
+                               "has already been applied during backward (construct the optimizer with fuse=False)")
         if self._fused_sumsq and self._sumsq is not None:
             total = self._sumsq
         else:

@@ -17,10 +17,28 @@ import torch
 
 
 class ShardedAdamW:
-    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8,
+                 fuse_into_reduce_scatter: bool = False):
+        """fuse_into_reduce_scatter: apply the update of each unit inside its gradient reduce-scatter kernel while
+        backward is still running (sm100 backend, world > 1).  Only legal when gradient clipping is disabled,
+        because clipping needs the norm of the whole gradient before any parameter changes."""
         self.model = model
         self.param_groups = [dict(lr=lr, weight_decay=weight_decay, betas=tuple(betas), eps=eps)]
         self.state: Dict[str, dict] = {u.name: {"step": 0} for u in model.all_units}
+        self.fused = bool(fuse_into_reduce_scatter and model.use_fsdp and model.world > 1 and model.split_master
+                          and getattr(model.backend, "supports_fused_adam", False))
+        self._done_in_backward = set()
+        if self.fused:
+            model._fused_opt = self
+
+    def fused_args(self, unit):
+        """Called by the engine when it enqueues the reduce-scatter of `unit` (fused mode)."""
+        g = self.param_groups[0]
+        st = self.state[unit.name]
+        st["step"] += 1
+        self._done_in_backward.add(unit.name)
+        return (unit.hi, unit.lo, unit.exp_avg, unit.exp_avg_sq,
+                [g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], float(st["step"])])
 
     def step(self) -> None:
         model, ops = self.model, self.model.ops
@@ -28,12 +46,15 @@ class ShardedAdamW:
         lr, wd, (b1, b2), eps = g["lr"], g["weight_decay"], g["betas"], g["eps"]
         clip = model._clip_coef
         for u in model.all_units:
+            if u.name in self._done_in_backward:
+                continue  # already updated inside its reduce-scatter kernel
             st = self.state[u.name]
             st["step"] += 1
             if model.split_master:
                 ops.adamw_split(u.hi, u.lo, u.exp_avg, u.exp_avg_sq, u.shard_grad, clip, lr, b1, b2, eps, wd, st["step"])
             else:
                 ops.adamw_fp32(u.master, u.exp_avg, u.exp_avg_sq, u.shard_grad, clip, lr, b1, b2, eps, wd, st["step"])
+        self._done_in_backward.clear()
         model._clip_coef = None
         model.backend.params_updated()
 

@@ -98,7 +98,9 @@ def train(rt: Runtime, cfg):
     rt.master_print(f"per-GPU (sharded) parameter num: {sum(p.numel() for p in parameters)}")
 
     # build optimizer and scheduler
-    optimizer = ShardedAdamW(model, lr=cfg.lr, weight_decay=cfg.weight_decay)
+    # without gradient clipping the AdamW update is fused into each unit's reduce-scatter kernel
+    optimizer = ShardedAdamW(model, lr=cfg.lr, weight_decay=cfg.weight_decay,
+                             fuse_into_reduce_scatter=cfg.clip_grad_norm <= 0)
     lr_scheduler = get_warmup_cosine_scheduler(
         optimizer, warmup_iteration=cfg.warmup_steps, max_iteration=len(train_dataset) // batch_size * num_epochs)
     rt.rendezvous("loaded optimizer")
