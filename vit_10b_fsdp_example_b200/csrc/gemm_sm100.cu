@@ -698,8 +698,10 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
         p.use_clc = env_clc;
         // n-tiles per raster group: the B panel of a group (group_n x 256 rows x K) should stay L2-resident
         // (~40 MB) while the A panels stream past it.  Measured DRAM reads, qkv (K=5120): 8->2.9 GB, 16->2.0 GB.
-        int g = K > 0 ? 81920 / K : 8;
-        g = g < 2 ? 2 : (g > 16 ? 16 : g);
+        // Deep-K panels (K >= 8192) cannot stay resident anyway: use a square-ish wave (74 tiles ~ 9 x 8) so that
+        // every panel fetched from DRAM is shared by as many co-running clusters as possible
+        // (wgrad K=32768: group 2 -> 17 GB of DRAM reads, group 8 -> ~7 GB).
+        const int g = (K > 0 && 81920 / K >= 12) ? 16 : 8;
         p.group_n = env_group > 0 ? env_group : g;
         p.hint_a = env_ha >= 0 ? env_ha : 0;
         p.hint_b = env_hb >= 0 ? env_hb : 0;
