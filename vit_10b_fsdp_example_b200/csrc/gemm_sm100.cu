@@ -40,7 +40,7 @@ namespace {
 constexpr int kBlockM = 128;  // rows per CTA (cluster tile = 256)
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kNumThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc + CLC scheduler, warp3 AG copier, warps4-11 epilogue
 constexpr int kEpiThreads = 128;
 constexpr int kCdBufs = 4;             // ring of 128x64 bf16 staging buffers for TMA stores
 constexpr int kCdBufBytes = 128 * 128;  // 128 rows x 128 B
@@ -153,12 +153,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);   // one multicast tcgen05.commit
-            mbar_init(&tmem_empty_bar[i], 8);  // 4 epilogue warps x 2 CTAs
+            mbar_init(&tmem_empty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
         }
         for (int i = 0; i < kClcStages; ++i) {
             mbar_init(&clc_full_bar[i], 1);    // the scheduler's expect_tx arrive (+16 B from the hardware)
-            // leader: producer + MMA + 4 epilogue warps + scheduler; peer: producer + 4 epilogue warps
-            mbar_init(&clc_empty_bar[i], 12);
+            // leader: producer + MMA + 8 epilogue warps + scheduler; peer: producer + 8 epilogue warps
+            mbar_init(&clc_empty_bar[i], 20);
         }
         fence_mbar_init();
     }
@@ -404,12 +404,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
         }
     } else if (warp_idx >= 4) {
         // ================================= Epilogue warps =================================
-        const uint32_t ew = warp_idx - 4;              // == warp_idx % 4: TMEM lane quarter of this warp
-        const uint32_t etid = threadIdx.x - 128;       // 0..127
+        // Two groups of four warps.  A warp may only touch the TMEM lane quarter (warp_idx % 4), so both groups
+        // cover all 128 rows and split the tile by 64-column chunks (group g takes chunks g, g+2): the epilogue of a
+        // tile takes half as long, which matters for the fat epilogues (dGELU, two outputs) and for the short-K
+        // attention GEMMs where the epilogue, not the MMA, sets the pace.  Each chunk is processed as two 32-column
+        // halves written straight into the swizzled staging buffer, which keeps the register count under the
+        // 168/thread a 384-thread CTA allows.
+        constexpr int kChunks = BLOCK_N / 64;
+        static_assert(kChunks >= 2, "both epilogue groups need at least one chunk");
+        const uint32_t eg = (warp_idx - 4) >> 2;       // epilogue group
+        const uint32_t ew = warp_idx & 3;              // TMEM lane quarter of this warp
+        const uint32_t etid = (threadIdx.x - 128) & 127;
         const uint32_t row_in_tile = ew * 32 + lane;   // accumulator row owned by this thread
+        const uint32_t bar_id = 1 + eg;
+        uint8_t* const grp_buf = smem_cd + eg * 2 * kCdBufBytes;  // two staging buffers per group
         const GemmEpilogue& e = p.epi;
+        const bool ext_is_aux = e.act == kActDGelu;
         uint32_t iter = 0;
-        uint32_t cd_idx = 0;  // ring position (identical on all epilogue threads)
+        uint32_t flip = 0;
         TileIter it = tile_begin();
         for (bool more = it.tile < total_tiles; more; more = tile_next(it, lane == 0), ++iter) {
             const int t = it.tile;
@@ -424,117 +436,108 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((ew * 32) << 16) + as * BLOCK_N;
+            const __nv_bfloat16* ext_row = nullptr;
+            if (ext_is_aux) {
+                ext_row = e.aux_in + static_cast<int64_t>(row) * e.ld_aux;
+            } else if (e.residual != nullptr) {
+                const int rrow = e.res_row_mod > 0 ? row % e.res_row_mod : row;
+                ext_row = e.residual + static_cast<int64_t>(rrow) * e.ld_res;
+            }
 
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 64; ++c) {
+            for (int c = eg; c < kChunks; c += 2) {
                 const int ncol0 = n0 + c * 64;
-                uint32_t acc_lo[32], acc_hi[32];
-                tmem_ld_32x32b_x32(taddr + c * 64, acc_lo);
-                tmem_ld_32x32b_x32(taddr + c * 64 + 32, acc_hi);
-                // Prefetch this thread's 64 per-row epilogue inputs (dGELU pre-activation or residual) while the
-                // TMEM load is in flight: 8 independent 16 B loads instead of 8 exposed round trips.
-                const bool ext_is_aux = e.act == kActDGelu;
-                const __nv_bfloat16* ext_row = nullptr;
-                if (ext_is_aux) {
-                    ext_row = e.aux_in + static_cast<int64_t>(row) * e.ld_aux;
-                } else if (e.residual != nullptr) {
-                    const int rrow = e.res_row_mod > 0 ? row % e.res_row_mod : row;
-                    ext_row = e.residual + static_cast<int64_t>(rrow) * e.ld_res;
+                const bool last_chunk = c + 2 >= kChunks;  // last TMEM read of this warp for the tile
+                if (ncol0 >= p.N) {  // tile-uniform: nothing to store, but the TMEM stage must still be released
+                    if (last_chunk) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                    }
+                    continue;
                 }
-                uint4 ext[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = ncol0 + j * 8;
-                    ext[j] = (ext_row != nullptr && row_ok && col < p.N)
-                                 ? *reinterpret_cast<const uint4*>(ext_row + col)
-                                 : make_uint4(0, 0, 0, 0);
-                }
-                tmem_ld_wait();
-                if (c == BLOCK_N / 64 - 1) {
-                    // accumulators are in registers: hand the TMEM stage back to the MMA warp early
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-                }
-                if (ncol0 >= p.N) continue;  // tile-uniform: whole chunk is out of range (nothing to store)
-
-                // ---- fused math, 8 columns (one 16 B bf16 vector) at a time ----
-                uint32_t out[32];  // 64 bf16 packed
-                uint32_t pre[32];  // pre-activation side output (only if has_aux_out)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = ncol0 + j * 8;
-                    const bool col_ok = col < p.N;
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int idx = j * 8 + q;
-                        v[q] = __uint_as_float(idx < 32 ? acc_lo[idx] : acc_hi[idx - 32]);
-                    }
-                    if (e.bias != nullptr && col_ok) {
-                        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(e.bias + col));
-                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[2 * q] += bf16_lo(bw[q]);
-                            v[2 * q + 1] += bf16_hi(bw[q]);
-                        }
-                    }
-                    if (e.has_aux_out) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) pre[j * 4 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-                    }
-                    if (e.act == kActGelu) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = gelu_erf(v[q]);
-                    } else if (e.act == kActDGelu) {
-                        const uint32_t uw[4] = {ext[j].x, ext[j].y, ext[j].z, ext[j].w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[2 * q] *= dgelu_erf(bf16_lo(uw[q]));
-                            v[2 * q + 1] *= dgelu_erf(bf16_hi(uw[q]));
-                        }
-                    }
-                    if (e.residual != nullptr && !ext_is_aux) {
-                        const uint32_t rw[4] = {ext[j].x, ext[j].y, ext[j].z, ext[j].w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[2 * q] += bf16_lo(rw[q]);
-                            v[2 * q + 1] += bf16_hi(rw[q]);
-                        }
-                    }
-                    if (!(row_ok && col_ok)) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = 0.f;  // keeps the column sums clean
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) out[j * 4 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-                }
-
-                // ---- stage through swizzled smem and TMA-store ----
-                const int n_stores = e.has_aux_out ? 2 : 1;
+                // staging buffer(s) of this group free again?
+                uint8_t* buf0 = grp_buf + (e.has_aux_out ? 0 : (flip & 1)) * kCdBufBytes;
+                uint8_t* buf1 = grp_buf + kCdBufBytes;
                 if (etid == 0) {
                     if (e.has_aux_out)
-                        tma_store_wait_read<kCdBufs - 2>();
+                        tma_store_wait_read<0>();
                     else
-                        tma_store_wait_read<kCdBufs - 1>();
+                        tma_store_wait_read<1>();
                 }
-                named_bar_sync(1, kEpiThreads);
-                uint8_t* buf0 = smem_cd + (cd_idx % kCdBufs) * kCdBufBytes;
-                uint8_t* buf1 = smem_cd + ((cd_idx + 1) % kCdBufs) * kCdBufBytes;
-                {
-                    const uint32_t rbase = smem_u32(buf0) + row_in_tile * 128;
-                    const uint32_t rbase1 = smem_u32(buf1) + row_in_tile * 128;
+                named_bar_sync(bar_id, kEpiThreads);
+                const uint32_t rbase = smem_u32(buf0) + row_in_tile * 128;
+                const uint32_t rbase1 = smem_u32(buf1) + row_in_tile * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t off = ((j ^ (row_in_tile & 7)) * 16);
-                        st_shared_v4(rbase + off, out[j * 4], out[j * 4 + 1], out[j * 4 + 2], out[j * 4 + 3]);
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(taddr + c * 64 + h * 32, acc);
+                    // per-row epilogue inputs (dGELU pre-activation or residual) are fetched while the TMEM load flies
+                    uint4 ext[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = ncol0 + h * 32 + j * 8;
+                        ext[j] = (ext_row != nullptr && row_ok && col < p.N)
+                                     ? *reinterpret_cast<const uint4*>(ext_row + col)
+                                     : make_uint4(0, 0, 0, 0);
+                    }
+                    tmem_ld_wait();
+                    if (last_chunk && h == 1) {
+                        // accumulators are in registers: hand the TMEM stage back to the MMA warp early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = ncol0 + h * 32 + j * 8;
+                        const bool col_ok = col < p.N;
+                        float v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[j * 8 + q]);
+                        if (e.bias != nullptr && col_ok) {
+                            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(e.bias + col));
+                            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[2 * q] += bf16_lo(bw[q]);
+                                v[2 * q + 1] += bf16_hi(bw[q]);
+                            }
+                        }
+                        const uint32_t off = (((h * 4 + j) ^ (row_in_tile & 7)) * 16);
                         if (e.has_aux_out)
-                            st_shared_v4(rbase1 + off, pre[j * 4], pre[j * 4 + 1], pre[j * 4 + 2], pre[j * 4 + 3]);
+                            st_shared_v4(rbase1 + off, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        if (e.act == kActGelu) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = gelu_erf(v[q]);
+                        } else if (ext_is_aux) {
+                            const uint32_t uw[4] = {ext[j].x, ext[j].y, ext[j].z, ext[j].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[2 * q] *= dgelu_erf(bf16_lo(uw[q]));
+                                v[2 * q + 1] *= dgelu_erf(bf16_hi(uw[q]));
+                            }
+                        }
+                        if (e.residual != nullptr && !ext_is_aux) {
+                            const uint32_t rw[4] = {ext[j].x, ext[j].y, ext[j].z, ext[j].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[2 * q] += bf16_lo(rw[q]);
+                                v[2 * q + 1] += bf16_hi(rw[q]);
+                            }
+                        }
+                        if (!(row_ok && col_ok)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = 0.f;  // keeps the column sums clean
+                        }
+                        st_shared_v4(rbase + off, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                     pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     }
                 }
+                // ---- swizzled staging buffer -> global through TMA ----
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(bar_id, kEpiThreads);
                 if (etid == 0) {
                     tma_store_4d(&tmap_d, buf0, ncol0, m0, bi, bo);
                     tma_store_commit();
@@ -558,7 +561,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
                     if (ncol0 + ccol < p.N)
                         atomicAdd(e.colsum + static_cast<int64_t>(bi) * e.colsum_bi_stride + ncol0 + ccol, s);
                 }
-                cd_idx += n_stores;
+                ++flip;
             }
         }
         if (etid == 0) tma_store_wait<0>();
@@ -695,7 +698,9 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
         static const int env_ha = getenv("B200_GEMM_HINT_A") ? atoi(getenv("B200_GEMM_HINT_A")) : -1;
         static const int env_hb = getenv("B200_GEMM_HINT_B") ? atoi(getenv("B200_GEMM_HINT_B")) : -1;
         static const int env_clc = getenv("B200_GEMM_CLC") ? atoi(getenv("B200_GEMM_CLC")) : 1;
-        p.use_clc = env_clc;
+        // dynamic scheduling pays for long tiles; for short-K (attention) tiles the try_cancel round trip would be
+        // on the critical path of every ~1 us tile, so those keep the static persistent schedule
+        p.use_clc = env_clc && K >= 1024;
         // n-tiles per raster group: the B panel of a group (group_n x 256 rows x K) should stay L2-resident
         // (~40 MB) while the A panels stream past it.  Measured DRAM reads, qkv (K=5120): 8->2.9 GB, 16->2.0 GB.
         // Deep-K panels (K >= 8192) cannot stay resident anyway: use a square-ish wave (74 tiles ~ 9 x 8) so that
