@@ -124,7 +124,7 @@ def _collectives_worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def _train_worker(rank, world, port, backend, out_path, flatten, reshard, clip=1.0, fuse_opt=False):
+def _train_worker(rank, world, port, backend, out_path, flatten, reshard, clip=1.0, fuse_opt=False, graph=False):
     dist = _init(rank, world, port)
     from vit_10b_fsdp_example_b200.config import ViTConfig
     from vit_10b_fsdp_example_b200.parallel import FSDPViT, ShardedAdamW
@@ -141,10 +141,20 @@ def _train_worker(rank, world, port, backend, out_path, flatten, reshard, clip=1
     target = torch.randint(0, 96, (8,), generator=g)
     lb = 8 // world
     losses, norms = [], []
+    gstep = None
+    if graph:
+        from vit_10b_fsdp_example_b200.parallel import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, opt, clip_grad_norm=clip, warmup=2)
     for _ in range(6):
-        loss = model.forward_backward(images[rank * lb:(rank + 1) * lb].to(dev), target[rank * lb:(rank + 1) * lb].to(dev))
-        norm = model.clip_grad_norm_(clip) if clip > 0 else torch.zeros(1)
-        opt.step()
+        xi, yi = images[rank * lb:(rank + 1) * lb].to(dev), target[rank * lb:(rank + 1) * lb].to(dev)
+        if gstep is not None:
+            loss = gstep(xi, yi)
+            norm = gstep.grad_norm if gstep.grad_norm is not None else torch.zeros(1)
+        else:
+            loss = model.forward_backward(xi, yi)
+            norm = model.clip_grad_norm_(clip) if clip > 0 else torch.zeros(1)
+            opt.step()
         lv = loss.detach().float().reshape(1).clone()
         dist.all_reduce(lv)
         losses.append(lv.item() / world)
@@ -203,6 +213,21 @@ def test_adamw_fused_into_reduce_scatter(tmp_path):
         _spawn(_train_worker, world, (backend, out, False, True, 0.0, fuse))
         outs[name] = json.load(open(out))
     a, b = outs["ref"], outs["fused"]
+    for x, y in zip(a["losses"], b["losses"]):
+        assert abs(x - y) < 0.03 * abs(x) + 0.02, (a, b)
+    assert b["losses"][-1] < b["losses"][0]
+
+
+def test_cuda_graph_step_two_gpus(tmp_path):
+    """Whole step (incl. the symmetric-memory collectives with device-side sequence numbers) as one CUDA graph."""
+    world = 2
+    _need_gpus(world)
+    outs = {}
+    for name, graph in (("eager", False), ("graph", True)):
+        out = str(tmp_path / f"{name}.json")
+        _spawn(_train_worker, world, ("sm100", out, False, True, 1.0, False, graph))
+        outs[name] = json.load(open(out))
+    a, b = outs["eager"], outs["graph"]
     for x, y in zip(a["losses"], b["losses"]):
         assert abs(x - y) < 0.03 * abs(x) + 0.02, (a, b)
     assert b["losses"][-1] < b["losses"][0]

@@ -55,6 +55,8 @@ def build_arg_parser() -> argparse.ArgumentParser:
                         help="processes to spawn when not launched by torchrun (0 = one per visible GPU, 1 on CPU)")
     parser.add_argument("--bench_json", type=str, default="", help="append per-log-step JSON lines to this file")
     parser.add_argument("--h2d_prefetch", type=int, default=2, help="batches staged ahead on the copy stream")
+    parser.add_argument("--cuda_graph", action="store_true",
+                        help="capture the whole training step (fwd, bwd, collectives, clip, AdamW) in one CUDA graph")
     return parser
 
 

@@ -131,14 +131,14 @@ void sumsq(Tensor x, Tensor out) {
 }
 
 void adamw_split(Tensor hi, Tensor lo, Tensor m, Tensor v, Tensor grad, OptT clip_coef, double lr, double beta1,
-                 double beta2, double eps, double wd, int64_t step) {
+                 double beta2, double eps, double wd, int64_t step, OptT hyper) {
     c10::cuda::CUDAGuard guard(hi.device());
     TORCH_CHECK(hi.scalar_type() == at::kBFloat16 && lo.scalar_type() == at::kShort, "hi: bf16, lo: int16");
     const bool gbf = grad.scalar_type() == at::kBFloat16;
     b200::adamw_split(reinterpret_cast<uint16_t*>(hi.data_ptr()), reinterpret_cast<int16_t*>(lo.data_ptr()),
                       f32_ptr(m), f32_ptr(v), grad.data_ptr(), gbf, hi.numel(),
                       clip_coef.has_value() ? f32_ptr(*clip_coef) : nullptr, (float)lr, (float)beta1, (float)beta2,
-                      (float)eps, (float)wd, (int)step, cur_stream());
+                      (float)eps, (float)wd, (int)step, cur_stream(), hyper.has_value() ? f32_ptr(*hyper) : nullptr);
 }
 
 void adamw_fp32(Tensor w, Tensor m, Tensor v, Tensor grad, OptT clip_coef, double lr, double beta1, double beta2,
@@ -214,14 +214,20 @@ void nvls_reduce_scatter(int64_t mc_ptr, int64_t rank, int64_t world, Tensor out
                               total_chunks, (float)scale, sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr,
                               (int)max_ctas, cur_stream(), fused ? &a : nullptr);
 }
-void signal_barrier(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, int64_t slot, int64_t seq) {
-    b200::signal_barrier(flag_ptrs, (int)rank, (int)world, (int)slot, (uint32_t)seq, cur_stream());
+inline uint32_t* seq_ptr(const OptT& t) {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kInt, "sequence counters: CUDA int32 tensor");
+    return reinterpret_cast<uint32_t*>(t->data_ptr());
+}
+void signal_barrier(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, int64_t slot, int64_t seq,
+                    OptT seq_dev) {
+    b200::signal_barrier(flag_ptrs, (int)rank, (int)world, (int)slot, (uint32_t)seq, cur_stream(), seq_ptr(seq_dev));
 }
 void allreduce_scalars(std::vector<int64_t> flag_ptrs, std::vector<int64_t> scratch_ptrs, int64_t rank, int64_t world,
-                       int64_t slot, int64_t seq, Tensor vals, int64_t op) {
+                       int64_t slot, int64_t seq, Tensor vals, int64_t op, OptT seq_dev, int64_t counter_idx) {
     c10::cuda::CUDAGuard guard(vals.device());
     b200::allreduce_scalars(flag_ptrs, scratch_ptrs, (int)rank, (int)world, (int)slot, (uint32_t)seq, f32_ptr(vals),
-                            (int)vals.numel(), (int)op, cur_stream());
+                            (int)vals.numel(), (int)op, cur_stream(), seq_ptr(seq_dev), (int)counter_idx);
 }
 int64_t ag_chunk_bytes() { return b200::ag_chunk_bytes(); }
 int64_t rs_chunk_elems() { return b200::rs_chunk_elems(); }

@@ -210,8 +210,14 @@ __global__ void __launch_bounds__(kCommThreads) reduce_scatter_kernel(PeerPtrs p
 }
 
 // flags layout in every rank's symmetric flag region: uint32 flags[slot][world]
-__global__ void signal_barrier_kernel(PeerPtrs flag_bases, int rank, int world, int slot, uint32_t seq) {
+// seq_dev (optional): per-slot sequence counters kept on the device (every rank advances them identically), so
+// the same launch can be replayed from a CUDA graph.
+__global__ void signal_barrier_kernel(PeerPtrs flag_bases, int rank, int world, int slot, uint32_t seq,
+                                      uint32_t* seq_dev) {
     const int r = threadIdx.x;
+    if (seq_dev != nullptr) seq = seq_dev[slot] + 1;
+    __syncwarp();
+    if (r == 0 && seq_dev != nullptr) seq_dev[slot] = seq;
     if (r >= world) return;
     __threadfence_system();
     uint32_t* remote = reinterpret_cast<uint32_t*>(flag_bases.p[r]) + slot * kMaxWorld + rank;
@@ -230,8 +236,15 @@ __global__ void signal_barrier_kernel(PeerPtrs flag_bases, int rank, int world, 
 // scratch layout in every rank's symmetric region: float scratch[slot][world][kMaxScalars]
 constexpr int kMaxScalars = 16;
 __global__ void allreduce_scalars_kernel(PeerPtrs flag_bases, PeerPtrs scratch_bases, int rank, int world, int slot,
-                                         uint32_t seq, float* __restrict__ vals, int k, int op) {
+                                         uint32_t seq, float* __restrict__ vals, int k, int op, uint32_t* seq_dev,
+                                         int counter_idx) {
     const int t = threadIdx.x;
+    if (seq_dev != nullptr) {  // slot alternates with the parity of the device-side sequence number
+        seq = seq_dev[counter_idx] + 1;
+        slot = slot + static_cast<int>(seq & 1u);
+    }
+    __syncthreads();
+    if (t == 0 && seq_dev != nullptr) seq_dev[counter_idx] = seq;
     // phase 1: thread (r, j) pushes vals[j] into peer r's scratch[slot][rank][j]
     if (t < world * k) {
         const int r = t / k, j = t % k;
@@ -326,16 +339,17 @@ void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const 
 }
 
 void signal_barrier(const std::vector<int64_t>& flag_ptrs, int rank, int world, int slot, uint32_t seq,
-                    cudaStream_t stream) {
-    signal_barrier_kernel<<<1, 32, 0, stream>>>(to_peers(flag_ptrs), rank, world, slot, seq);
+                    cudaStream_t stream, uint32_t* seq_dev) {
+    signal_barrier_kernel<<<1, 32, 0, stream>>>(to_peers(flag_ptrs), rank, world, slot, seq, seq_dev);
     check_launch("signal_barrier");
 }
 
 void allreduce_scalars(const std::vector<int64_t>& flag_ptrs, const std::vector<int64_t>& scratch_ptrs, int rank,
-                       int world, int slot, uint32_t seq, float* vals, int k, int op, cudaStream_t stream) {
+                       int world, int slot, uint32_t seq, float* vals, int k, int op, cudaStream_t stream,
+                       uint32_t* seq_dev, int counter_idx) {
     if (k > kMaxScalars) throw std::runtime_error("allreduce_scalars: at most 16 values");
     allreduce_scalars_kernel<<<1, 256, 0, stream>>>(to_peers(flag_ptrs), to_peers(scratch_ptrs), rank, world, slot, seq,
-                                                   vals, k, op);
+                                                   vals, k, op, seq_dev, counter_idx);
     check_launch("allreduce_scalars");
 }
 

@@ -27,10 +27,13 @@ void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const 
                          int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream,
                          const AdamFuse* adam = nullptr);
 // flags: uint32 [slot][16] per rank; scratch: float [slot][16][16] per rank (both in symmetric memory)
+// seq_dev != nullptr: sequence numbers come from (and are advanced in) device memory -> CUDA-graph replayable.
+// For allreduce_scalars the flag/scratch slot is then `slot + (seq & 1)`.
 void signal_barrier(const std::vector<int64_t>& flag_ptrs, int rank, int world, int slot, uint32_t seq,
-                    cudaStream_t stream);
+                    cudaStream_t stream, uint32_t* seq_dev = nullptr);
 void allreduce_scalars(const std::vector<int64_t>& flag_ptrs, const std::vector<int64_t>& scratch_ptrs, int rank,
-                       int world, int slot, uint32_t seq, float* vals, int k, int op, cudaStream_t stream);
+                       int world, int slot, uint32_t seq, float* vals, int k, int op, cudaStream_t stream,
+                       uint32_t* seq_dev = nullptr, int counter_idx = 0);
 int64_t ag_chunk_bytes();
 int64_t rs_chunk_elems();
 int comm_max_world();

@@ -465,8 +465,14 @@ __global__ void __launch_bounds__(256) adamw_split_kernel(uint16_t* __restrict__
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const GradT* __restrict__ grad, int64_t n,
                                                           const float* __restrict__ clip_coef, float lr, float beta1,
-                                                          float beta2, float eps, float wd, float bc1, float bc2) {
+                                                          float beta2, float eps, float wd, float bc1, float bc2,
+                                                          const float* __restrict__ hyper) {
     const float coef = clip_coef != nullptr ? *clip_coef : 1.0f;
+    if (hyper != nullptr) {  // lr and step live on the device so the launch can sit inside a CUDA graph
+        lr = hyper[0];
+        bc1 = 1.f - powf(beta1, hyper[1]);
+        bc2 = 1.f - powf(beta2, hyper[1]);
+    }
     const float inv_bc1 = 1.f / bc1, inv_bc2 = 1.f / bc2, decay = 1.f - lr * wd;
     const int64_t n4 = n / 4;
     for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n4;
@@ -696,17 +702,18 @@ void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stre
 
 void adamw_split(uint16_t* hi, int16_t* lo, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n,
                  const float* clip_coef, float lr, float beta1, float beta2, float eps, float wd, int step,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const float* hyper) {
     const int grid = static_cast<int>(std::min<int64_t>((n / 4 + 255) / 256 + 1, sm_count() * 16));
     if (grid == 0) return;
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
     if (grad_is_bf16)
         adamw_split_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(hi, lo, m, v, static_cast<const __nv_bfloat16*>(grad),
-                                                                   n, clip_coef, lr, beta1, beta2, eps, wd, bc1, bc2);
+                                                                   n, clip_coef, lr, beta1, beta2, eps, wd, bc1, bc2,
+                                                                   hyper);
     else
         adamw_split_kernel<float><<<grid, 256, 0, stream>>>(hi, lo, m, v, static_cast<const float*>(grad), n, clip_coef,
-                                                           lr, beta1, beta2, eps, wd, bc1, bc2);
+                                                           lr, beta1, beta2, eps, wd, bc1, bc2, hyper);
     check_launch("adamw_split");
 }
 

@@ -28,9 +28,10 @@ void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S
 void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream);
 void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stream);
 
+// hyper (optional, device): [lr, step] override the host values (CUDA-graph friendly)
 void adamw_split(uint16_t* hi, int16_t* lo, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n,
                  const float* clip_coef, float lr, float beta1, float beta2, float eps, float wd, int step,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const float* hyper = nullptr);
 void adamw_fp32(float* w, float* m, float* v, const void* grad, bool grad_is_bf16, int64_t n, const float* clip_coef,
                 float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t stream);
 void split_fp32(const float* w, uint16_t* hi, int16_t* lo, int64_t n, cudaStream_t stream);

@@ -262,8 +262,9 @@ def adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
     _C.adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)
 
 
-def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
-    _C.adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)
+def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int, hyper=None):
+    """hyper: optional device tensor [lr, step] that overrides the host scalars (CUDA-graph replay)."""
+    _C.adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step, hyper)
 
 
 def split_fp32(w, hi, lo):

@@ -213,7 +213,7 @@ def merge_fp32(hi, lo, w):
     w.copy_(bits.view(torch.float32))
 
 
-def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int):
+def adamw_split(hi, lo, m, v, grad, clip, lr, beta1, beta2, eps, wd, step: int, hyper=None):
     w = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
     merge_fp32(hi, lo, w)
     adamw_fp32(w, m, v, grad, clip, lr, beta1, beta2, eps, wd, step)

@@ -127,7 +127,9 @@ class Sm100Backend(TorchDistBackend):
         self._peer = {}      # data_ptr of a symmetric tensor -> list of peer base pointers
         self._mc = {}        # data_ptr -> multicast base pointer (0 if unsupported)
         self._seg_cache = {}
-        self._seq = {}       # slot -> sequence number
+        # per-slot sequence numbers live on the device (advanced inside the kernels), so every collective launch is
+        # replayable from a CUDA graph; all ranks issue the same sequence of collectives, hence identical counters
+        self._seq_dev = torch.zeros(16, dtype=torch.int32, device=device)
         self.group_name = dist.group.WORLD.group_name
         ctrl = self._symm_alloc(self.FLAG_BYTES, torch.uint8)
         ctrl.zero_()
@@ -167,13 +169,9 @@ class Sm100Backend(TorchDistBackend):
         t.zero_()
         return t
 
-    def _next_seq(self, slot: int) -> int:
-        self._seq[slot] = self._seq.get(slot, 0) + 1
-        return self._seq[slot]
-
     def device_barrier(self, slot: int = 0) -> None:
         """Stream-ordered cross-GPU barrier on the current stream (flags in symmetric memory)."""
-        self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, self._next_seq(slot))
+        self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, 0, self._seq_dev)
 
     # ---- segment tables (device int64), built once per (layout, purpose) ----
     def _ag_table(self, layout: UnitLayout, esize: int, exclude=()):
@@ -263,9 +261,9 @@ class Sm100Backend(TorchDistBackend):
     def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
         if self.world > 1:
             assert t.dtype == torch.float32 and t.numel() <= 16
-            seq = self._next_seq(3)
-            self._C.allreduce_scalars(self._flag_ptrs, self._scratch_ptrs, self.rank, self.world, 4 + (seq & 1), seq,
-                                      t, 0 if op == "sum" else 1)
+            # flag / scratch slot 4 or 5, alternating with the device-side sequence number (counter 3)
+            self._C.allreduce_scalars(self._flag_ptrs, self._scratch_ptrs, self.rank, self.world, 4, 0, t,
+                                      0 if op == "sum" else 1, self._seq_dev, 3)
         return t
 
     def params_updated(self) -> None:

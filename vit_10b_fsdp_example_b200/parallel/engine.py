@@ -104,6 +104,7 @@ class FSDPViT:
         self._fused_sumsq = False
         self.step_count = 0
         self.fuse_all_gather = fuse_all_gather
+        self._unrecorded = set()  # ids of events created but never recorded (must not be waited on during capture)
         self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
 
         # ---- streams ----
@@ -213,10 +214,11 @@ class FSDPViT:
     def _record(self, ev):
         if self.is_cuda:
             ev.record(torch.cuda.current_stream())
+            self._unrecorded.discard(id(ev))
         return ev
 
     def _wait(self, ev):
-        if self.is_cuda and ev is not None:
+        if self.is_cuda and ev is not None and id(ev) not in self._unrecorded:
             torch.cuda.current_stream().wait_event(ev)
 
     # ------------------------------------------------------------------------------------------------
@@ -319,12 +321,27 @@ class FSDPViT:
         self.drop.training = False
         return self
 
+    def _begin_step(self) -> None:
+        """Fork the communication stream from the compute stream.  Under CUDA-graph capture this is what pulls the
+        side stream into the capture; stale cross-step events are dropped because everything of the previous step
+        has been joined back into the compute stream (and a replayed graph is ordered after the previous one)."""
+        if not self.is_cuda or self._alias:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            self._param_buf_free = [self._new_event() for _ in self._param_bufs]
+            self._grad_buf_free = [self._new_event() for _ in self._grad_bufs]
+            self._unrecorded = set(id(e) for e in self._param_buf_free + self._grad_buf_free)
+        fork = self._record(self._new_event())
+        with self._on_comm():
+            self._wait(fork)
+
     def forward_backward(self, images: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One micro-step: loss, and this rank's (mean-reduced) shard gradients in ``unit.shard_grad``."""
         cfg, ops = self.cfg, self.ops
         B = images.shape[0]
         blocks = self.units
         self.drop.step = self.step_count
+        self._begin_step()
         if self._fused_sumsq:
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         # -------- forward --------

@@ -30,6 +30,17 @@ class ShardedAdamW:
         self._done_in_backward = set()
         if self.fused:
             model._fused_opt = self
+        # device-resident [lr, step]: lets the AdamW launches be replayed from a CUDA graph (see parallel/graph.py)
+        self.hyper = None
+        if model.is_cuda and model.split_master:
+            self.hyper = torch.zeros(2, dtype=torch.float32, device=model.device)
+            self._lr_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.lr_on_device = False  # True while a CUDA-graph owner keeps hyper[0] up to date itself
+
+    def push_lr(self) -> None:
+        """Copy the current host learning rate into the device hyper-parameter block (async, pinned source)."""
+        self._lr_pinned[0] = float(self.param_groups[0]["lr"])
+        self.hyper[0:1].copy_(self._lr_pinned, non_blocking=True)
 
     def fused_args(self, unit):
         """Called by the engine when it enqueues the reduce-scatter of `unit` (fused mode)."""
@@ -45,13 +56,19 @@ class ShardedAdamW:
         g = self.param_groups[0]
         lr, wd, (b1, b2), eps = g["lr"], g["weight_decay"], g["betas"], g["eps"]
         clip = model._clip_coef
+        hyper = self.hyper if not self._done_in_backward else None
+        if hyper is not None:
+            if not self.lr_on_device:
+                self.push_lr()
+            hyper[1:2].add_(1.0)  # device-side step counter (all units share the step count)
         for u in model.all_units:
             if u.name in self._done_in_backward:
                 continue  # already updated inside its reduce-scatter kernel
             st = self.state[u.name]
             st["step"] += 1
             if model.split_master:
-                ops.adamw_split(u.hi, u.lo, u.exp_avg, u.exp_avg_sq, u.shard_grad, clip, lr, b1, b2, eps, wd, st["step"])
+                ops.adamw_split(u.hi, u.lo, u.exp_avg, u.exp_avg_sq, u.shard_grad, clip, lr, b1, b2, eps, wd, st["step"],
+                                hyper)
             else:
                 ops.adamw_fp32(u.master, u.exp_avg, u.exp_avg_sq, u.shard_grad, clip, lr, b1, b2, eps, wd, st["step"])
         self._done_in_backward.clear()
@@ -77,6 +94,8 @@ class ShardedAdamW:
             self.state[u.name]["step"] = int(st["step"])
             u.exp_avg.copy_(st["exp_avg"])
             u.exp_avg_sq.copy_(st["exp_avg_sq"])
+        if self.hyper is not None and self.model.all_units:
+            self.hyper[1] = float(self.state[self.model.all_units[0].name]["step"])
         for g, sg in zip(self.param_groups, sd["param_groups"]):
             g.update({k: (tuple(v) if k == "betas" else v) for k, v in sg.items()})
 

@@ -13,7 +13,7 @@ import torch
 from .config import ViTConfig
 from .data import build_datasets
 from .launch import Runtime
-from .parallel import FSDPViT, ShardedAdamW
+from .parallel import FSDPViT, GraphedTrainStep, ShardedAdamW
 from .utils import SmoothedValue, get_warmup_cosine_scheduler
 from .utils.checkpoint import load_ckpt, save_ckpt
 
@@ -99,8 +99,10 @@ def train(rt: Runtime, cfg):
 
     # build optimizer and scheduler
     # without gradient clipping the AdamW update is fused into each unit's reduce-scatter kernel
+    use_graph = bool(getattr(cfg, "cuda_graph", False)) and device.type == "cuda"
     optimizer = ShardedAdamW(model, lr=cfg.lr, weight_decay=cfg.weight_decay,
-                             fuse_into_reduce_scatter=cfg.clip_grad_norm <= 0)
+                             fuse_into_reduce_scatter=cfg.clip_grad_norm <= 0 and not use_graph)
+    graphed = GraphedTrainStep(model, optimizer, cfg.clip_grad_norm) if use_graph else None
     lr_scheduler = get_warmup_cosine_scheduler(
         optimizer, warmup_iteration=cfg.warmup_steps, max_iteration=len(train_dataset) // batch_size * num_epochs)
     rt.rendezvous("loaded optimizer")
@@ -126,6 +128,27 @@ def train(rt: Runtime, cfg):
         if is_cuda:
             ev_prev.record()
         for step, (data, target) in enumerate(train_loader):
+            if graphed is not None:
+                # whole step (fwd, bwd, collectives, clip, AdamW) replayed as one CUDA graph
+                loss = graphed(data, target)
+                lr_scheduler.step()
+                optimizer.zero_grad(set_to_none=True)
+                t_new = time.time()
+                time_step_elapsed, time_step_b = t_new - time_step_b, t_new
+                smoothed_time.update(time_step_elapsed, batch_size=1)
+                is_first_iter = epoch == cfg.resume_epoch + 1 and step == 0
+                if is_first_iter or (step + 1) % cfg.log_step_interval == 0:
+                    lr = optimizer.param_groups[0]["lr"]
+                    ev_now = torch.cuda.Event(enable_timing=True)
+                    ev_now.record()
+                    ev_now.synchronize()
+                    span = 1 if is_first_iter else cfg.log_step_interval
+                    step_ms = rt.mesh_reduce("step_ms", ev_prev.elapsed_time(ev_now) / span, max)
+                    ev_prev = ev_now
+                    run_logging(rt, cfg, epoch, step, smoothed_loss, smoothed_time, loss, lr, step_ms, batch_size)
+                if cfg.max_steps and step + 1 >= cfg.max_steps:
+                    break
+                continue
             # 1+2. forward, loss, backward (explicit hand-written backward; gradients end up reduce-scattered)
             loss = model.forward_backward(data, target)
             if not cfg.run_without_fsdp:
