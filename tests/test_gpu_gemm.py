@@ -58,11 +58,12 @@ def test_mn_major_a_k_major_b():
     _close(d, at.float().t() @ b.float().t())
 
 
-def test_fused_epilogues():
+@pytest.mark.parametrize("K", [512, 2048])  # 512: stand-alone GELU kernels, 2048: fused in the GEMM epilogue
+def test_fused_epilogues(K):
     ops = _ops()
     from vit_10b_fsdp_example_b200.ops import torch_ops
 
-    M, N, K = 640, 1024, 512
+    M, N = 640, 1024
     x, w, b, r = _rand(M, K), _rand(N, K, scale=0.05), _rand(N), _rand(M, N)
     y, pre = ops.linear_fwd(x, w, b, act="gelu", residual=r, want_preact=True)
     yr, prer = torch_ops.linear_fwd(x.float(), w.float(), b.float(), act="gelu", residual=r.float(), want_preact=True)
@@ -74,7 +75,8 @@ def test_fused_epilogues():
     y2r = torch_ops.linear_fwd(x.float(), w.float(), b.float(), residual=tab.float(), res_row_mod=128)
     _close(y2, y2r)
     # dgelu + column sums
-    dy, w2, u = _rand(M, N), _rand(N, K, scale=0.05), _rand(M, K)
+    N2 = K  # reduction length of the dgrad GEMM decides fused vs stand-alone dGELU
+    dy, w2, u = _rand(M, N2), _rand(N2, 768, scale=0.05), _rand(M, 768)
     dx, cs = ops.linear_dgrad(dy, w2, dgelu_preact=u, want_colsum=True)
     dxr, csr = torch_ops.linear_dgrad(dy.float(), w2.float(), dgelu_preact=u.float(), want_colsum=True)
     _close(dx, dxr)

@@ -117,6 +117,15 @@ void im2col(Tensor img, Tensor cols, int64_t P) {
                  (int)cols.size(1), cur_stream());
 }
 
+void gelu_fwd(Tensor u, Tensor g) {
+    c10::cuda::CUDAGuard guard(u.device());
+    b200::gelu_fwd(bf16_ptr(u), bf16_mut(g), u.numel(), cur_stream());
+}
+void dgelu_mul(Tensor dg, Tensor u, Tensor du) {
+    c10::cuda::CUDAGuard guard(u.device());
+    b200::dgelu_mul(bf16_ptr(dg), bf16_ptr(u), bf16_mut(du), u.numel(), cur_stream());
+}
+
 void colsum(Tensor x, Tensor out) {
     c10::cuda::CUDAGuard guard(x.device());
     const int C = (int)x.size(-1);
@@ -243,6 +252,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("softmax_bwd", &softmax_bwd);
     m.def("cross_entropy", &cross_entropy);
     m.def("im2col", &im2col);
+    m.def("gelu_fwd", &gelu_fwd);
+    m.def("dgelu_mul", &dgelu_mul);
     m.def("colsum", &colsum);
     m.def("sumsq", &sumsq);
     m.def("adamw_split", &adamw_split);

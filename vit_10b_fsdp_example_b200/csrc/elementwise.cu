@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -251,6 +252,213 @@ __global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_kernel(const __nv_bfloat
                 if (dxsum != nullptr) atomicAdd(dxsum + idx * 8 + q, acc_dx[idx * 8 + q]);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm for narrow rows (D <= 2048): a row is handled by TPR threads (one 16 B vector each), a 256-thread CTA
+// works on 256/TPR rows at once, and a thread keeps the column accumulators of its 8 columns in registers.
+// The wide-row kernels above keep one row per CTA, which leaves most threads idle and serialises on two block
+// barriers per row when D is only 1024 (ViT-L): 136 us -> memory-bound.
+// ------------------------------------------------------------------------------------------------
+template <int TPR>
+__device__ __forceinline__ void group_sum2(float& a, float& b, float* red, int row_slot) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if constexpr (TPR > 32) {
+        constexpr int kWarps = TPR / 32;
+        const int w = (threadIdx.x % TPR) / 32, l = threadIdx.x % 32;
+        __syncthreads();
+        if (l == 0) {
+            red[(row_slot * kWarps + w) * 2] = a;
+            red[(row_slot * kWarps + w) * 2 + 1] = b;
+        }
+        __syncthreads();
+        a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+            a += red[(row_slot * kWarps + i) * 2];
+            b += red[(row_slot * kWarps + i) * 2 + 1];
+        }
+    }
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_small_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ gamma,
+                                                                  const __nv_bfloat16* __restrict__ beta,
+                                                                  __nv_bfloat16* __restrict__ y,
+                                                                  float* __restrict__ mean_out,
+                                                                  float* __restrict__ rstd_out, int rows, int D,
+                                                                  float eps) {
+    __shared__ float red[2 * (kLnThreads / 32)];
+    constexpr int kRowsPerCta = kLnThreads / TPR;
+    const int nvec = D / 8;
+    const int slot = threadIdx.x / TPR, idx = threadIdx.x % TPR;
+    const bool active = idx < nvec;
+    const float inv_d = 1.0f / static_cast<float>(D);
+    float g[8], bta[8];
+    if (active) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + idx), bta);
+    }
+    const int iters = (rows + gridDim.x * kRowsPerCta - 1) / (gridDim.x * kRowsPerCta);
+    for (int itn = 0; itn < iters; ++itn) {
+        const int row = (itn * gridDim.x + blockIdx.x) * kRowsPerCta + slot;
+        const bool ok = active && row < rows;
+        float f[8];
+        if (ok) {
+            unpack8(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * D)[idx], f);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+        }
+        float s = 0.f, dummy = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += f[q];
+        group_sum2<TPR>(s, dummy, red, slot);
+        const float mean = s * inv_d;
+        float ss = 0.f;
+        if (ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ss += (f[q] - mean) * (f[q] - mean);
+        }
+        group_sum2<TPR>(ss, dummy, red, slot);
+        const float rstd = rsqrtf(ss * inv_d + eps);
+        if (ok) {
+            if (idx == 0) {
+                mean_out[row] = mean;
+                rstd_out[row] = rstd;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = (f[q] - mean) * rstd * g[q] + bta[q];
+            reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * D)[idx] = pack8(f);
+        }
+    }
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(kLnThreads) ln_bwd_small_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                  const __nv_bfloat16* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ gamma,
+                                                                  const float* __restrict__ mean_in,
+                                                                  const float* __restrict__ rstd_in,
+                                                                  const __nv_bfloat16* __restrict__ dres,
+                                                                  __nv_bfloat16* __restrict__ dx,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  float* __restrict__ dxsum, int rows, int D) {
+    __shared__ float red[2 * (kLnThreads / 32)];
+    constexpr int kRowsPerCta = kLnThreads / TPR;
+    const int nvec = D / 8;
+    const int slot = threadIdx.x / TPR, idx = threadIdx.x % TPR;
+    const bool active = idx < nvec;
+    const float inv_d = 1.0f / static_cast<float>(D);
+    float gam[8], dg[8], db[8], dxs[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) gam[q] = 0.f, dg[q] = 0.f, db[q] = 0.f, dxs[q] = 0.f;
+    if (active) unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + idx), gam);
+    const int iters = (rows + gridDim.x * kRowsPerCta - 1) / (gridDim.x * kRowsPerCta);
+    for (int itn = 0; itn < iters; ++itn) {
+        const int row = (itn * gridDim.x + blockIdx.x) * kRowsPerCta + slot;
+        const bool ok = active && row < rows;
+        const int64_t base = static_cast<int64_t>(row) * D;
+        float xf[8], df[8], rf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xf[q] = 0.f, df[q] = 0.f, rf[q] = 0.f;
+        float mean = 0.f, rstd = 0.f;
+        if (ok) {
+            unpack8(reinterpret_cast<const uint4*>(x + base)[idx], xf);
+            unpack8(reinterpret_cast<const uint4*>(dy + base)[idx], df);
+            if (dres != nullptr) unpack8(reinterpret_cast<const uint4*>(dres + base)[idx], rf);
+            mean = mean_in[row];
+            rstd = rstd_in[row];
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float xhat = (xf[q] - mean) * rstd;
+            const float gq = df[q] * gam[q];
+            s1 += gq;
+            s2 += gq * xhat;
+            dg[q] += df[q] * xhat;
+            db[q] += df[q];
+        }
+        group_sum2<TPR>(s1, s2, red, slot);
+        s1 *= inv_d;
+        s2 *= inv_d;
+        if (ok) {
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float xhat = (xf[q] - mean) * rstd;
+                o[q] = rf[q] + rstd * (df[q] * gam[q] - s1 - xhat * s2);
+            }
+            const uint4 packed = pack8(o);
+            reinterpret_cast<uint4*>(dx + base)[idx] = packed;
+            if (dxsum != nullptr) {
+                float ob[8];
+                unpack8(packed, ob);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dxs[q] += ob[q];
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            atomicAdd(dgamma + idx * 8 + q, dg[q]);
+            atomicAdd(dbeta + idx * 8 + q, db[q]);
+            if (dxsum != nullptr) atomicAdd(dxsum + idx * 8 + q, dxs[q]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone exact GELU / dGELU.  For short-K GEMMs (ViT-L: K = 1024) the activation math does not fit under the
+// MMA time of a tile, so the fused epilogue would run the tensor cores at half speed; the op layer then uses the
+// plain GEMM plus these memory-bound kernels (for ViT-10B, K = 5120, the activations stay fused in the epilogue).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float erf_poly(float z, float& e) {
+    const float az = fabsf(z);
+    const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+    e = __expf(-az * az);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    return copysignf(1.0f - poly * t * e, z);
+}
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ g,
+                                                       int64_t nvec) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(u)[i], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float e;
+            f[q] = 0.5f * f[q] * (1.0f + erf_poly(f[q] * 0.70710678118654752f, e));
+        }
+        reinterpret_cast<uint4*>(g)[i] = pack8(f);
+    }
+}
+
+__global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __restrict__ dg,
+                                                        const __nv_bfloat16* __restrict__ u,
+                                                        __nv_bfloat16* __restrict__ du, int64_t nvec) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float f[8], d[8];
+        unpack8(reinterpret_cast<const uint4*>(u)[i], f);
+        unpack8(reinterpret_cast<const uint4*>(dg)[i], d);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float e;
+            const float cdf = 0.5f * (1.0f + erf_poly(f[q] * 0.70710678118654752f, e));
+            d[q] *= fmaf(f[q] * 0.3989422804014327f, e, cdf);
+        }
+        reinterpret_cast<uint4*>(du)[i] = pack8(d);
     }
 }
 
@@ -599,9 +807,27 @@ int sm_count() {
         default: throw std::runtime_error("layernorm: width > 8192 not supported"); \
     }
 
+#define LN_SMALL_DISPATCH(KERNEL, ...)                                                  \
+    {                                                                                   \
+        const int nv = D / 8;                                                           \
+        const int tpr = nv <= 32 ? 32 : (nv <= 64 ? 64 : (nv <= 128 ? 128 : 256));      \
+        const int rows_per = kLnThreads / tpr;                                          \
+        const int grid = std::min((rows + rows_per - 1) / rows_per, sm_count() * 6);    \
+        if (tpr == 32) KERNEL<32><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__);        \
+        else if (tpr == 64) KERNEL<64><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__);   \
+        else if (tpr == 128) KERNEL<128><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__); \
+        else KERNEL<256><<<grid, kLnThreads, 0, stream>>>(__VA_ARGS__);                 \
+    }
+
 void layernorm_fwd(const __nv_bfloat16* x, const __nv_bfloat16* gamma, const __nv_bfloat16* beta, __nv_bfloat16* y,
                    float* mean, float* rstd, int rows, int D, float eps, cudaStream_t stream) {
     if (D % 8 != 0) throw std::runtime_error("layernorm: width must be a multiple of 8");
+    static const bool ln_small = getenv("B200_LN_SMALL") == nullptr || atoi(getenv("B200_LN_SMALL")) != 0;
+    if (D <= 2048 && ln_small) {
+        LN_SMALL_DISPATCH(ln_fwd_small_kernel, x, gamma, beta, y, mean, rstd, rows, D, eps);
+        check_launch("layernorm_fwd_small");
+        return;
+    }
     const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
     const int grid = std::min(rows, sm_count() * 8);
     LN_DISPATCH(chunks, ln_fwd_kernel, x, gamma, beta, y, mean, rstd, rows, D, eps);
@@ -625,6 +851,12 @@ void layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const __nv_b
                    const float* rstd, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                    float* dxsum, int rows, int D, cudaStream_t stream) {
     if (D % 8 != 0) throw std::runtime_error("layernorm: width must be a multiple of 8");
+    static const bool ln_small = getenv("B200_LN_SMALL") == nullptr || atoi(getenv("B200_LN_SMALL")) != 0;
+    if (D <= 2048 && ln_small) {
+        LN_SMALL_DISPATCH(ln_bwd_small_kernel, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D);
+        check_launch("layernorm_bwd_small");
+        return;
+    }
     const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
     const size_t smem = static_cast<size_t>(dxsum != nullptr ? 3 : 2) * D * sizeof(float);
     const int per_sm = std::max<int>(1, std::min<int>(3, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
@@ -677,6 +909,22 @@ void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S
     else
         im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(img), cols, B, S, P, Kpad);
     check_launch("im2col");
+}
+
+void gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* g, int64_t n, cudaStream_t stream) {
+    if (n % 8 != 0) throw std::runtime_error("gelu: element count must be a multiple of 8");
+    const int grid = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    gelu_fwd_kernel<<<grid, 256, 0, stream>>>(u, g, n / 8);
+    check_launch("gelu_fwd");
+}
+
+void dgelu_mul(const __nv_bfloat16* dg, const __nv_bfloat16* u, __nv_bfloat16* du, int64_t n, cudaStream_t stream) {
+    if (n % 8 != 0) throw std::runtime_error("dgelu: element count must be a multiple of 8");
+    const int grid = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    dgelu_mul_kernel<<<grid, 256, 0, stream>>>(dg, u, du, n / 8);
+    check_launch("dgelu_mul");
 }
 
 void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream) {

@@ -25,6 +25,8 @@ void cross_entropy(const __nv_bfloat16* logits, const int64_t* target, __nv_bflo
 void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S, int P, int Kpad,
             cudaStream_t stream);
 
+void gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* g, int64_t n, cudaStream_t stream);
+void dgelu_mul(const __nv_bfloat16* dg, const __nv_bfloat16* u, __nv_bfloat16* du, int64_t n, cudaStream_t stream);
 void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream);
 void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stream);
 

@@ -50,6 +50,11 @@ def launch_count() -> int:
     return _C.count
 
 ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+# GELU / dGELU are fused into the GEMM epilogue only when the reduction is deep enough to hide the math
+# (ViT-10B: K = 5120 fused; ViT-L: K = 1024 -> plain GEMM + stand-alone elementwise kernel, measured 1.5x faster)
+import os as _os
+
+FUSE_ACT_MIN_K = int(_os.environ.get("B200_FUSE_ACT_MIN_K", "2048"))
 
 # SM carve-out for compute kernels while a communication kernel runs next to them (0 = all SMs).
 _max_ctas = 0
@@ -126,6 +131,14 @@ def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_ro
     shards of `w` over NVLink while it computes."""
     M, K = x.shape
     N = w.shape[0]
+    if act == "gelu" and K < FUSE_ACT_MIN_K and N % 8 == 0 and ag is None:
+        # short K: the activation math would not fit under a tile's MMA time -> plain GEMM + memory-bound GELU
+        pre = linear_fwd(x, w, bias, residual=None)
+        y = torch.empty_like(pre)
+        _C.gelu_fwd(pre, y)
+        if residual is not None:
+            y += residual
+        return (y, pre) if want_preact else y
     x, w = _tma_rows(x), _tma_rows(w)
     ldy = _pad8(N)
     y = torch.empty(M, ldy, dtype=x.dtype, device=x.device)
@@ -142,6 +155,12 @@ def linear_fwd(x, w, bias=None, act: Optional[str] = None, residual=None, res_ro
 def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
     M, N = dy.shape
     K = w.shape[1]
+    if dgelu_preact is not None and N < FUSE_ACT_MIN_K and K % 8 == 0:
+        dx = linear_dgrad(dy, w)
+        _C.dgelu_mul(dx, dgelu_preact, dx)
+        if want_colsum:
+            return dx, colsum(dx)
+        return dx
     dy, w = _tma_rows(dy), _tma_rows(w)
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
     cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if want_colsum else None
