@@ -27,3 +27,27 @@ def test_attention_fwd_bwd(B, N, H, hd):
     dqkvr, csr = to.attention_bwd(dout.float(), qkv.float(), pr, B, N, H, hd, want_colsum=True)
     _close(dqkv, dqkvr)
     _close(cs, csr, rel=5e-2)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 256, 4, 160), (3, 196, 3, 64), (2, 64, 2, 128), (1, 256, 2, 64)])
+def test_fused_attention_forward(B, N, H, hd):
+    """Fused tcgen05 kernel (S/P never leave the SM) vs the fp32 reference; with and without the P side output."""
+    from vit_10b_fsdp_example_b200.ops import cuda_ops as co, torch_ops as to
+
+    assert co._C.attention_fwd_supported(N, hd)
+    co.FUSED_ATTENTION_HD160 = True  # exercise the hd=160 instantiation too (off by default: slower than un-fused)
+    D = H * hd
+    qkv = (torch.randn(B * N, 3 * D, device="cuda") * 0.7).to(torch.bfloat16)
+    outr, pr = to.attention_fwd(qkv.float(), B, N, H, hd)
+    out, p = co.attention_fwd(qkv, B, N, H, hd, need_p=True)
+    _close(out, outr)
+    _close(p.view(B, H, N, -1)[..., :N], pr)
+    out2, p2 = co.attention_fwd(qkv, B, N, H, hd, need_p=False)
+    assert p2 is None
+    assert torch.equal(out2, out)
+    lse = torch.empty(B * H, N, device="cuda")
+    out3 = torch.empty_like(out)
+    co._C.attention_fwd(qkv, out3, lse, None, B, N, H, hd)
+    q, k, _ = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    lser = torch.logsumexp((q @ k.transpose(-1, -2)) * hd ** -0.5, dim=-1).reshape(B * H, N)
+    assert (lse - lser).abs().max().item() < 2e-2

@@ -8,6 +8,7 @@
 #include <optional>
 #include <vector>
 
+#include "attention_sm100.h"
 #include "comm.h"
 #include "elementwise.h"
 #include "gemm_sm100.h"
@@ -96,6 +97,16 @@ void softmax_fwd(Tensor s, int64_t rows, int64_t n, int64_t ld, double scale) {
 void softmax_bwd(Tensor dp, Tensor p, int64_t rows, int64_t n, int64_t ld, double scale) {
     c10::cuda::CUDAGuard guard(p.device());
     b200::softmax_bwd(bf16_mut(dp), bf16_ptr(p), rows, (int)n, ld, (float)scale, cur_stream());
+}
+
+bool attention_fwd_supported(int64_t N, int64_t hd) { return b200::attention_fwd_supported((int)N, (int)hd); }
+
+void attention_fwd(Tensor qkv, Tensor out, OptT lse, OptT probs, int64_t B, int64_t N, int64_t H, int64_t hd) {
+    c10::cuda::CUDAGuard guard(qkv.device());
+    TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && out.is_contiguous(), "attention_fwd: bad layouts");
+    b200::attention_fwd(bf16_ptr(qkv), qkv.stride(0), bf16_mut(out), lse.has_value() ? f32_ptr(*lse) : nullptr,
+                        probs.has_value() ? bf16_mut(*probs) : nullptr, probs.has_value() ? probs->size(2) : 0, (int)B,
+                        (int)N, (int)H, (int)hd, cur_stream());
 }
 
 void cross_entropy(Tensor logits, Tensor target, OptT dlogits, Tensor loss, OptT correct) {
@@ -250,6 +261,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("layernorm_bwd", &layernorm_bwd);
     m.def("softmax_fwd", &softmax_fwd);
     m.def("softmax_bwd", &softmax_bwd);
+    m.def("attention_fwd", &attention_fwd);
+    m.def("attention_fwd_supported", &attention_fwd_supported);
     m.def("cross_entropy", &cross_entropy);
     m.def("im2col", &im2col);
     m.def("gelu_fwd", &gelu_fwd);

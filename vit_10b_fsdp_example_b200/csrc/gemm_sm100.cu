@@ -610,7 +610,8 @@ struct TmapKeyHash {
 };
 
 // 4-D bf16 tensor map: dims (inner, outer, batch_inner, batch_outer), box (box_inner, box_outer, 1, 1).
-CUtensorMap make_tmap(const GemmOperand& op, int64_t inner, int64_t outer, int box_inner, int box_outer) {
+CUtensorMap make_tmap(const GemmOperand& op, int64_t inner, int64_t outer, int box_inner, int box_outer,
+                      int swizzle_bytes = 128) {
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     static std::mutex mu;
     TmapKey key;
@@ -618,7 +619,7 @@ CUtensorMap make_tmap(const GemmOperand& op, int64_t inner, int64_t outer, int b
     key.ptr = reinterpret_cast<uint64_t>(op.ptr);
     key.d[0] = inner, key.d[1] = outer, key.d[2] = op.nb_inner, key.d[3] = op.nb_outer;
     key.s[0] = op.ld, key.s[1] = op.stride_b_inner, key.s[2] = op.stride_b_outer;
-    key.box[0] = box_inner, key.box[1] = box_outer;
+    key.box[0] = box_inner, key.box[1] = box_outer + (swizzle_bytes << 16);
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -638,7 +639,10 @@ CUtensorMap make_tmap(const GemmOperand& op, int64_t inner, int64_t outer, int b
     cuuint32_t box[4] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer), 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult res = get_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides,
-                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                         : CU_TENSOR_MAP_SWIZZLE_32B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) {
         char msg[256];
@@ -745,6 +749,11 @@ void launch(const GemmOperand& A, const GemmOperand& B, const GemmOperand& D, co
 }
 
 }  // namespace
+
+CUtensorMap make_tensor_map_4d(const GemmOperand& op, int64_t inner, int64_t outer, int box_inner, int box_outer,
+                               int swizzle_bytes) {
+    return make_tmap(op, inner, outer, box_inner, box_outer, swizzle_bytes);
+}
 
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,

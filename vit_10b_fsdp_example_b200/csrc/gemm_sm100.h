@@ -1,5 +1,6 @@
 // Host API of the sm_100a tcgen05 GEMM (see gemm_sm100.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -50,5 +51,9 @@ struct GemmAgFuse {
 void gemm_bf16(const GemmOperand& A, int major_a, const GemmOperand& B, int major_b, const GemmOperand& D,
                const GemmOperand* aux_out, int M, int N, int K, const GemmEpilogue& epi, int block_n, int max_ctas,
                cudaStream_t stream, const GemmAgFuse* ag = nullptr);
+
+// Cached 4-D bf16 TMA descriptor: dims (inner, outer, op.nb_inner, op.nb_outer), box (box_inner, box_outer, 1, 1).
+CUtensorMap make_tensor_map_4d(const GemmOperand& op, int64_t inner, int64_t outer, int box_inner, int box_outer,
+                               int swizzle_bytes);
 
 }  // namespace b200

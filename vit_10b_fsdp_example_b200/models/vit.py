@@ -140,7 +140,7 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[
         masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
         a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
     else:
-        a, P = ops.attention_fwd(qkv, B, N, H, hd)
+        a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p=save)
     if use_drop and pm > 0:
         # timm feeds `drop` to both proj_drop and the two MLP dropouts
         masks["proj"] = drop.mask(x.shape, pm, site + 1, x.device)

@@ -112,7 +112,7 @@ def colsum(x):
 # Attention core (timm Attention: softmax(q k^T * hd^-0.5) v, no mask) -- run_vit_training.py:134
 # qkv is the packed [T, 3*D] projection; head h of q lives at columns [h*hd, (h+1)*hd).
 # ------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0):
+def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0, need_p: bool = True):
     D = H * hd
     q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)  # [B, H, N, hd]
     s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
