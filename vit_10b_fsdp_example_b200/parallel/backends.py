@@ -115,8 +115,10 @@ class Sm100Backend(TorchDistBackend):
         super().__init__(world, rank, device)
         from ..ops import native
 
+        import os
+
         self._C = native.load()
-        self.comm_ctas = comm_ctas
+        self.comm_ctas = int(os.environ.get("B200_COMM_CTAS", comm_ctas))  # SMs the stand-alone collectives may take
         self.use_nvls = False
         if world == 1:  # single GPU: nothing to communicate, gathered buffers alias the shards
             return
@@ -138,7 +140,7 @@ class Sm100Backend(TorchDistBackend):
         self._scratch_ptrs = [p + 32 * 1024 for p in self._flag_ptrs]
         torch.cuda.synchronize()
         dist.barrier()
-        self.use_nvls = all(v != 0 for v in self._mc.values())
+        self.use_nvls = all(v != 0 for v in self._mc.values()) and os.environ.get("B200_NVLS", "1") != "0"
 
     # ---- symmetric allocation ----
     def _symm_alloc(self, numel: int, dtype) -> torch.Tensor:

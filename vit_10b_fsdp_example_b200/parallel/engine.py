@@ -103,7 +103,9 @@ class FSDPViT:
         self._sumsq = None
         self._fused_sumsq = False
         self.step_count = 0
-        self.fuse_all_gather = fuse_all_gather
+        import os
+
+        self.fuse_all_gather = fuse_all_gather and os.environ.get("B200_FUSE_AG", "1") != "0"
         self._unrecorded = set()  # ids of events created but never recorded (must not be waited on during capture)
         self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
 
