@@ -26,7 +26,8 @@ def run(rank, world, port, opts, out_path):
     model = FSDPViT(cfg, world=world, rank=rank, dtype=torch.float32,
                     reshard_after_forward=opts.get("reshard", True), flatten_parameters=opts.get("flatten", False),
                     grad_ckpt=opts.get("grad_ckpt", True), run_without_fsdp=opts.get("no_fsdp", False),
-                    shard_on_cpu=opts.get("shard_on_cpu", False), seed=opts.get("seed", 0))
+                    shard_on_cpu=opts.get("shard_on_cpu", False), seed=opts.get("seed", 0),
+                    ckpt_keep_blocks=opts.get("keep_blocks", 0))
     opt = ShardedAdamW(model, lr=opts.get("lr", 1e-2), weight_decay=0.1)
     sched = get_warmup_cosine_scheduler(opt, 2, 100)
     global_batch = opts.get("global_batch", 8)

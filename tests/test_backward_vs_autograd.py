@@ -31,15 +31,36 @@ def test_grads_match_autograd(grad_ckpt, flatten):
     assert torch.allclose(logits.double(), ref_logits.detach(), atol=1e-4)
 
 
+@pytest.mark.parametrize("keep", [1, 99])
+def test_lean_activation_keeping_matches_autograd(keep):
+    """Memory-aware checkpointing: blocks that keep the lean activation set (and re-materialise LN outputs, P and
+    gelu(u) in backward) must produce the same gradients as autograd."""
+    torch.manual_seed(0)
+    cfg = tiny_cfg()
+    model = FSDPViT(cfg, dtype=torch.float32, grad_ckpt=True, ckpt_keep_blocks=keep, seed=3)
+    images = torch.randn(4, 3, cfg.image_size, cfg.image_size)
+    target = torch.tensor([1, 5, 7, 2])
+    loss = model.forward_backward(images, target)
+    got = full_grads_of(model)
+    params = {k: v.double().requires_grad_(True) for k, v in full_params_of(model).items()}
+    ref_loss, _ = autograd_vit_loss(cfg, params, images.double(), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
+    for name, p in params.items():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert (got[name].double() - g).abs().max().item() / (g.abs().max().item() + 1e-8) < 2e-4, name
+
+
 def test_dropout_recompute_is_consistent():
     """With dropout > 0 the checkpoint recompute must regenerate the same masks as the first forward."""
     cfg = tiny_cfg(pos_dropout=0.1, att_dropout=0.1, mlp_dropout=0.1)
     images = torch.randn(4, 3, cfg.image_size, cfg.image_size)
     target = torch.tensor([1, 5, 7, 2])
     grads = []
-    for ckpt in (True, False):
-        model = FSDPViT(cfg, dtype=torch.float32, grad_ckpt=ckpt, seed=3)
+    for ckpt, keep in ((True, 0), (False, 0), (True, 1)):
+        model = FSDPViT(cfg, dtype=torch.float32, grad_ckpt=ckpt, ckpt_keep_blocks=keep, seed=3)
         model.forward_backward(images, target)
         grads.append(full_grads_of(model))
-    for k in grads[0]:
-        assert torch.allclose(grads[0][k], grads[1][k], atol=1e-6), k
+    for other in grads[1:]:
+        for k in grads[0]:
+            assert torch.allclose(grads[0][k], other[k], atol=1e-6), k

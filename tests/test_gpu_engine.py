@@ -107,3 +107,36 @@ def test_cuda_graph_step_matches_eager():
     for k in sde:
         assert (sde[k] - sdg[k]).abs().mean().item() < 2e-3, k
         assert (sde[k] - sdg[k]).abs().max().item() < 4e-2, k
+
+
+def _full_grads(model):
+    return {u.name: u.shard_grad.float().clone() for u in model.all_units}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("heads,dim", [(2, 320), (4, 256)])
+def test_lean_blocks_vs_recompute(heads, dim):
+    from vit_10b_fsdp_example_b200.config import ViTConfig
+    from vit_10b_fsdp_example_b200.parallel import FSDPViT
+
+    cfg = ViTConfig(image_size=112, patch_size=14, embed_dim=dim, num_heads=heads, num_blocks=3, mlp_ratio=4.0,
+                    num_classes=96)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 3, 112, 112, generator=g).to(dev)
+    y = torch.randint(0, 96, (8,), generator=g).to(dev)
+    grads, losses = [], []
+    for keep in (0, 2, 3):
+        model = FSDPViT(cfg, device=dev, dtype=torch.bfloat16, seed=4, ckpt_keep_blocks=keep)
+        losses.append(model.forward_backward(x, y).item())
+        grads.append(_full_grads(model))
+    assert abs(losses[0] - losses[1]) < 1e-3 and abs(losses[0] - losses[2]) < 1e-3
+    for other in grads[1:]:
+        for k in grads[0]:
+            a, b = grads[0][k], other[k]
+            assert (a - b).norm().item() <= 2e-2 * a.norm().item() + 1e-6, k
+    auto = FSDPViT(cfg, device=dev, dtype=torch.bfloat16, seed=4, ckpt_keep_blocks=-1)
+    auto.forward_backward(x, y)
+    assert auto.keep_blocks == -1
+    auto.forward_backward(x, y)
+    assert 0 <= auto.keep_blocks <= 3

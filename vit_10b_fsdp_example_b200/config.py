@@ -44,6 +44,10 @@ def build_arg_parser() -> argparse.ArgumentParser:
     parser.add_argument("--run_without_fsdp", action="store_true", dest="run_without_fsdp")
     parser.add_argument("--shard_on_cpu", action="store_true", dest="shard_on_cpu")
     # ---- B200 extras (not in the reference; defaults keep reference semantics) ----
+    parser.add_argument("--ckpt_keep_blocks", type=int, default=-1,
+                        help="with --grad_ckpt: how many (top) blocks keep a lean activation set instead of being "
+                             "recomputed in backward; -1 = as many as the free HBM allows (measured after step 1), "
+                             "0 = checkpoint every block exactly like the reference")
     parser.add_argument("--dtype", type=str, default="auto", choices=["auto", "bf16", "fp32"],
                         help="compute dtype; auto = bf16 on CUDA, fp32 on CPU")
     parser.add_argument("--backend", type=str, default="auto", choices=["auto", "sm100", "nccl", "gloo"],

@@ -125,9 +125,12 @@ def _apply_mask(t, mask, p):
 # ------------------------------------------------------------------------------------------------
 # Transformer block
 # ------------------------------------------------------------------------------------------------
-def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[DropoutCtx] = None,
+def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[DropoutCtx] = None,
                   block_idx: int = 0):
-    """x: [B*N, D] -> y: [B*N, D].  With save=True also returns the tensors backward needs."""
+    """x: [B*N, D] -> y: [B*N, D].  With save=True also returns the tensors backward needs; save="lean" keeps
+    only what a GEMM would have to recompute (x, qkv, attention output, x1, fc1 pre-activation: 10 [T, D] units
+    instead of ~17.6) and block_backward re-materialises h1 / P / h2 / gelu(u) with memory-bound kernels."""
+    lean = save == "lean"
     N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
     pa, pm = cfg.att_dropout, cfg.mlp_dropout
     use_drop = drop is not None and drop.training and (pa > 0 or pm > 0)
@@ -140,7 +143,7 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[
         masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
         a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
     else:
-        a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p=save)
+        a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p=bool(save) and not lean)
     if use_drop and pm > 0:
         # timm feeds `drop` to both proj_drop and the two MLP dropouts
         masks["proj"] = drop.mask(x.shape, pm, site + 1, x.device)
@@ -164,6 +167,8 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save: bool, drop: Optional[
         y = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"], residual=x1)
     if not save:
         return y, None
+    if lean:
+        return y, dict(lean=True, x=x, m1=m1, r1=r1, qkv=qkv, a=a, x1=x1, m2=m2, r2=r2, u=u, masks=masks)
     saved = dict(x=x, m1=m1, r1=r1, h1=h1, qkv=qkv, P=P, a=a, x1=x1, m2=m2, r2=r2, h2=h2, u=u, g=g, masks=masks)
     return y, saved
 
@@ -178,6 +183,7 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
     pa, pm = cfg.att_dropout, cfg.mlp_dropout
     masks = s["masks"]
+    lean = s.get("lean", False)
     # ---- MLP ----
     if "fc2" in masks:
         dt = _apply_mask(dy, masks["fc2"], pm)
@@ -185,7 +191,14 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     else:
         dt = dy
         G["mlp.fc2.bias"].copy_(dy_colsum)
-    ops.linear_wgrad(dt, s["g"], out=G["mlp.fc2.weight"])
+    if lean:
+        g = ops.gelu_fwd(s["u"])
+        if "fc1" in masks:
+            g = _apply_mask(g, masks["fc1"], pm)
+    else:
+        g = s["g"]
+    ops.linear_wgrad(dt, g, out=G["mlp.fc2.weight"])
+    del g
     if "fc1" in masks:
         dg = _apply_mask(ops.linear_dgrad(dt, p["mlp.fc2.weight"]), masks["fc1"], pm)
         du = (dg.float() * ops_dgelu(ops, s["u"])).to(dy.dtype)
@@ -193,7 +206,9 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     else:
         du, db1 = ops.linear_dgrad(dt, p["mlp.fc2.weight"], dgelu_preact=s["u"], want_colsum=True)
     G["mlp.fc1.bias"].copy_(db1)
-    ops.linear_wgrad(du, s["h2"], out=G["mlp.fc1.weight"])
+    h2 = ops.ln_fwd(s["x1"], p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)[0] if lean else s["h2"]
+    ops.linear_wgrad(du, h2, out=G["mlp.fc1.weight"])
+    del h2
     dh2 = ops.linear_dgrad(du, p["mlp.fc1.weight"])
     del du
     dx1, dn2w, dn2b, dx1_sum = ops.ln_bwd(dh2, s["x1"], p["norm2.weight"], s["m2"], s["r2"], dres=dy, want_dxsum=True)
@@ -209,6 +224,8 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
         G["attn.proj.bias"].copy_(dx1_sum)
     ops.linear_wgrad(dt, s["a"], out=G["attn.proj.weight"])
     da = ops.linear_dgrad(dt, p["attn.proj.weight"])
+    if lean:
+        s["P"] = ops.attention_probs(s["qkv"], B, N, H, hd)
     if "att" in masks:
         dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True, drop_mask=masks["att"],
                                         drop_scale=1.0 / (1.0 - pa))
@@ -216,7 +233,10 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
         dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True)
     del da
     G["attn.qkv.bias"].copy_(dbqkv)
-    ops.linear_wgrad(dqkv, s["h1"], out=G["attn.qkv.weight"])
+    s["P"] = None
+    h1 = ops.ln_fwd(s["x"], p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)[0] if lean else s["h1"]
+    ops.linear_wgrad(dqkv, h1, out=G["attn.qkv.weight"])
+    del h1
     dh1 = ops.linear_dgrad(dqkv, p["attn.qkv.weight"])
     del dqkv
     dx, dn1w, dn1b, dx_sum = ops.ln_bwd(dh1, s["x"], p["norm1.weight"], s["m1"], s["r1"], dres=dx1, want_dxsum=True)

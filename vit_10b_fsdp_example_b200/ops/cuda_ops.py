@@ -180,6 +180,12 @@ def linear_wgrad(dy, x, out=None):
     return out
 
 
+def gelu_fwd(u):
+    g = torch.empty_like(u)
+    _C.gelu_fwd(u, g)
+    return g
+
+
 def colsum(x):
     out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
     _C.colsum(x, out)
@@ -227,6 +233,20 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
     gemm_raw(p, ldp, 0, v, ld3, 1, out, D, N, hd, N,
              batch=(H, B, N * ldp, H * N * ldp, hd, N * ld3, hd, N * D))
     return out, p
+
+
+def attention_probs(qkv, B: int, N: int, H: int, hd: int):
+    """P = softmax(Q K^T / sqrt(hd)) alone: re-materialised in backward for blocks that kept only qkv."""
+    D = H * hd
+    ldp = _pad8(N)
+    p = torch.empty(B * H, N, ldp, dtype=qkv.dtype, device=qkv.device)
+    if ldp != N:
+        p[:, :, N:].zero_()
+    ld3 = qkv.stride(0)
+    gemm_raw(qkv[:, :D], ld3, 0, qkv[:, D:2 * D], ld3, 0, p, ldp, N, N, hd,
+             batch=(H, B, hd, N * ld3, hd, N * ld3, N * ldp, H * N * ldp))
+    _C.softmax_fwd(p, B * H * N, N, ldp, hd ** -0.5)
+    return p
 
 
 def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,

@@ -57,6 +57,10 @@ def gelu(x):
     return F.gelu(x)  # exact erf form, like timm's nn.GELU
 
 
+def gelu_fwd(u):
+    return F.gelu(_f32(u)).to(u.dtype)
+
+
 def dgelu(u):
     uf = _f32(u)
     cdf = 0.5 * (1.0 + torch.erf(uf * (1.0 / math.sqrt(2.0))))
@@ -122,6 +126,12 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
         pd = (p * drop_mask * drop_scale).to(qkv.dtype)
     o = (_f32(pd) @ v).permute(0, 2, 1, 3).reshape(B * N, D).to(qkv.dtype)
     return o, p
+
+
+def attention_probs(qkv, B: int, N: int, H: int, hd: int):
+    """P alone (re-materialised in backward when only qkv was kept)."""
+    q, k, _ = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    return torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1).to(qkv.dtype)
 
 
 def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,

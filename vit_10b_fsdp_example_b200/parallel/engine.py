@@ -71,7 +71,8 @@ class FSDPViT:
     def __init__(self, vcfg: ViTConfig, *, world: int = 1, rank: int = 0, device=None, dtype=torch.float32,
                  reshard_after_forward: bool = True, flatten_parameters: bool = False, grad_ckpt: bool = True,
                  run_without_fsdp: bool = False, shard_on_cpu: bool = False, backend: str = "torchdist",
-                 seed: int = 0, init_device: str = "cpu", verbose_build=None, fuse_all_gather: bool = True):
+                 seed: int = 0, init_device: str = "cpu", verbose_build=None, fuse_all_gather: bool = True,
+                 ckpt_keep_blocks: int = 0):
         self.cfg = vcfg
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.dtype = dtype
@@ -83,6 +84,11 @@ class FSDPViT:
         self.reshard_after_forward = reshard_after_forward
         self.flatten_parameters = flatten_parameters
         self.grad_ckpt = grad_ckpt
+        # Memory-aware activation checkpointing: the top `keep_blocks` blocks keep a lean set of activations
+        # (10 [T, D] tensors: nothing a GEMM would have to recompute) and skip the forward recompute in backward;
+        # the blocks below are checkpointed as in the reference (run_vit_training.py:171 checkpoint_module).
+        # -1 = decide after the first step from the HBM that is actually free (see _auto_keep_blocks).
+        self.keep_blocks = int(ckpt_keep_blocks) if grad_ckpt else 0
         self.shard_on_cpu = shard_on_cpu
         self.training = True
         self.is_cuda = self.device.type == "cuda"
@@ -337,11 +343,47 @@ class FSDPViT:
         with self._on_comm():
             self._wait(fork)
 
+    def lean_bytes_per_block(self, batch: int) -> int:
+        """HBM a block's lean activation set occupies: x, qkv (3), attention out, x1, fc1 pre-activation."""
+        cfg = self.cfg
+        units = 6.0 + cfg.mlp_ratio
+        return int(batch * cfg.num_patches * cfg.embed_dim * units * torch.empty((), dtype=self.dtype).element_size())
+
+    def _auto_keep_blocks(self, batch: int) -> int:
+        """Called once, after the first (fully checkpointed) step: the caching allocator now holds that step's
+        transient peak, so whatever the device still reports free can hold kept activations.  The margin covers
+        allocator fragmentation; the result is the minimum over ranks so every GPU runs the same schedule."""
+        if not self.is_cuda:
+            return 0
+        import os
+
+        if self.dp_world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(torch.zeros(1, device=self.device))  # communicator buffers exist before we measure
+        torch.cuda.synchronize(self.device)
+        free, total = torch.cuda.mem_get_info(self.device)
+        margin = int(float(os.environ.get("B200_CKPT_MARGIN_GB", "8")) * 2 ** 30) + total // 50
+        k = max(0, min(len(self.units), (free - margin) // max(1, self.lean_bytes_per_block(batch))))
+        if self.dp_world > 1:
+            t = torch.tensor([k], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            k = int(t.item())
+        return int(k)
+
     def forward_backward(self, images: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One micro-step: loss, and this rank's (mean-reduced) shard gradients in ``unit.shard_grad``."""
         cfg, ops = self.cfg, self.ops
         B = images.shape[0]
         blocks = self.units
+        if self.keep_blocks < 0:
+            if self.step_count == 0 or (self.is_cuda and torch.cuda.is_current_stream_capturing()):
+                n_keep = 0
+            else:
+                self.keep_blocks = n_keep = self._auto_keep_blocks(B)
+        else:
+            n_keep = min(self.keep_blocks, len(blocks))
+        keep_from = len(blocks) - n_keep if self.grad_ckpt else 0  # blocks >= keep_from are not recomputed
         self.drop.step = self.step_count
         self._begin_step()
         if self._fused_sumsq:
@@ -360,11 +402,12 @@ class FSDPViT:
                 self._issue_gather(blocks[i + 1], fuse=True)
             self._wait_gather(u)
             p = self._views(u)
-            if self.grad_ckpt:
+            if i < keep_from:
                 ckpt.append(x)
                 x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
             else:
-                x, s = vit.block_forward(ops, cfg, p, x, B, save=True, drop=self.drop, block_idx=i)
+                x, s = vit.block_forward(ops, cfg, p, x, B, save="lean" if self.grad_ckpt else True, drop=self.drop,
+                                         block_idx=i)
                 saved_all.append(s)
             if self.reshard_after_forward and i != len(blocks) - 1:
                 self._release_params(u)  # the last block is needed again immediately by backward
@@ -376,12 +419,13 @@ class FSDPViT:
         del head_saved, logits, dlogits
         for i in range(len(blocks) - 1, -1, -1):
             u = blocks[i]
-            self._issue_gather(u, fuse=self.grad_ckpt)
+            # a recomputed block runs its qkv / fc1 forward GEMMs again and those pull their own weights
+            self._issue_gather(u, fuse=i < keep_from)
             if i - 1 >= 0:
-                self._issue_gather(blocks[i - 1], fuse=self.grad_ckpt)  # prefetch for the backward sweep
+                self._issue_gather(blocks[i - 1], fuse=i - 1 < keep_from)  # prefetch for the backward sweep
             self._wait_gather(u)
             p = self._views(u)
-            if self.grad_ckpt:
+            if i < keep_from:
                 xin = ckpt.pop()
                 _, s = vit.block_forward(ops, cfg, p, xin, B, save=True, drop=self.drop, block_idx=i)
             else:

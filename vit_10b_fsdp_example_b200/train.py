@@ -38,6 +38,8 @@ def build_fsdp_vit_model(cfg, rt: Runtime) -> FSDPViT:
         reshard_after_forward=cfg.reshard_after_forward, flatten_parameters=cfg.flatten_parameters,
         grad_ckpt=cfg.grad_ckpt, run_without_fsdp=cfg.run_without_fsdp, shard_on_cpu=cfg.shard_on_cpu,
         backend=resolve_backend(cfg, rt.device), seed=cfg.seed, verbose_build=rt.master_print,
+        ckpt_keep_blocks=getattr(cfg, "ckpt_keep_blocks", 0) if rt.device.type == "cuda" else
+        max(0, getattr(cfg, "ckpt_keep_blocks", 0)),
     )
 
 
