@@ -263,7 +263,8 @@ def run_ours(args):
                                       f"{' off' if args.no_grad_ckpt else ''}, backend {model.backend.name})",
                        "activation_ckpt": ("off" if args.no_grad_ckpt else
                                            f"memory-aware: {kept} of {blocks} blocks keep a lean activation set "
-                                           f"(no GEMM recompute), {blocks - kept} are recomputed in backward"),
+                                           f"(no GEMM recompute; of those {model.keep_extras} also keep P / LN "
+                                           f"outputs / gelu(u)), {blocks - kept} are recomputed in backward"),
                        "optimizer": "AdamW + clip_grad_norm 1.0 + warmup-cosine, every step",
                        "cuda_graph": bool(use_graph),
                        "l2": "no explicit flush: each step streams ~20 GB of bf16 weights plus activations (>> 126 MB L2)",

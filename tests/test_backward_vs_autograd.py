@@ -31,13 +31,16 @@ def test_grads_match_autograd(grad_ckpt, flatten):
     assert torch.allclose(logits.double(), ref_logits.detach(), atol=1e-4)
 
 
-@pytest.mark.parametrize("keep", [1, 99])
-def test_lean_activation_keeping_matches_autograd(keep):
+@pytest.mark.parametrize("keep,extras", [(1, None), (99, None), (99, {"P": 1, "h": 99, "g": 0}),
+                                         (99, {"P": 99, "h": 0, "g": 1})])
+def test_lean_activation_keeping_matches_autograd(keep, extras):
     """Memory-aware checkpointing: blocks that keep the lean activation set (and re-materialise LN outputs, P and
     gelu(u) in backward) must produce the same gradients as autograd."""
     torch.manual_seed(0)
     cfg = tiny_cfg()
     model = FSDPViT(cfg, dtype=torch.float32, grad_ckpt=True, ckpt_keep_blocks=keep, seed=3)
+    if extras is not None:  # some of the kept blocks also keep P / LN outputs / gelu(u)
+        model.keep_extras = extras
     images = torch.randn(4, 3, cfg.image_size, cfg.image_size)
     target = torch.tensor([1, 5, 7, 2])
     loss = model.forward_backward(images, target)

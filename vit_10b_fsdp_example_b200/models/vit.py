@@ -129,8 +129,16 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
                   block_idx: int = 0):
     """x: [B*N, D] -> y: [B*N, D].  With save=True also returns the tensors backward needs; save="lean" keeps
     only what a GEMM would have to recompute (x, qkv, attention output, x1, fc1 pre-activation: 10 [T, D] units
-    instead of ~17.6) and block_backward re-materialises h1 / P / h2 / gelu(u) with memory-bound kernels."""
-    lean = save == "lean"
+    instead of ~17.6) and block_backward re-materialises h1 / P / h2 / gelu(u) with memory-bound kernels.
+    save may also be a set of extras to keep on top of the lean set: "P" (attention probabilities),
+    "h" (both LayerNorm outputs), "g" (gelu(u)); True == all three."""
+    do_save = save is not False and save is not None
+    if save is True:
+        extras = frozenset(("P", "h", "g"))
+    elif not do_save or isinstance(save, str):
+        extras = frozenset()
+    else:
+        extras = frozenset(save)
     N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
     pa, pm = cfg.att_dropout, cfg.mlp_dropout
     use_drop = drop is not None and drop.training and (pa > 0 or pm > 0)
@@ -143,7 +151,7 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
         masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
         a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
     else:
-        a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p=bool(save) and not lean)
+        a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p="P" in extras)
     if use_drop and pm > 0:
         # timm feeds `drop` to both proj_drop and the two MLP dropouts
         masks["proj"] = drop.mask(x.shape, pm, site + 1, x.device)
@@ -152,7 +160,7 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
     else:
         x1 = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"], residual=x)
     h2, m2, r2 = ops.ln_fwd(x1, p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)
-    if save:
+    if do_save:
         g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", want_preact=True,
                               ag=ag.get("mlp.fc1.weight"))
     else:
@@ -165,11 +173,15 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
         y = (x1.float() + _apply_mask(t, masks["fc2"], pm).float()).to(x.dtype)
     else:
         y = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"], residual=x1)
-    if not save:
+    if not do_save:
         return y, None
-    if lean:
-        return y, dict(lean=True, x=x, m1=m1, r1=r1, qkv=qkv, a=a, x1=x1, m2=m2, r2=r2, u=u, masks=masks)
-    saved = dict(x=x, m1=m1, r1=r1, h1=h1, qkv=qkv, P=P, a=a, x1=x1, m2=m2, r2=r2, h2=h2, u=u, g=g, masks=masks)
+    saved = dict(x=x, m1=m1, r1=r1, qkv=qkv, a=a, x1=x1, m2=m2, r2=r2, u=u, masks=masks)
+    if "P" in extras:
+        saved["P"] = P
+    if "h" in extras:
+        saved["h1"], saved["h2"] = h1, h2
+    if "g" in extras:
+        saved["g"] = g
     return y, saved
 
 
@@ -183,7 +195,6 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     N, H, hd = cfg.num_patches, cfg.num_heads, cfg.head_dim
     pa, pm = cfg.att_dropout, cfg.mlp_dropout
     masks = s["masks"]
-    lean = s.get("lean", False)
     # ---- MLP ----
     if "fc2" in masks:
         dt = _apply_mask(dy, masks["fc2"], pm)
@@ -191,12 +202,11 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     else:
         dt = dy
         G["mlp.fc2.bias"].copy_(dy_colsum)
-    if lean:
+    g = s.pop("g", None)
+    if g is None:  # not kept: re-materialise from the pre-activation
         g = ops.gelu_fwd(s["u"])
         if "fc1" in masks:
             g = _apply_mask(g, masks["fc1"], pm)
-    else:
-        g = s["g"]
     ops.linear_wgrad(dt, g, out=G["mlp.fc2.weight"])
     del g
     if "fc1" in masks:
@@ -206,7 +216,9 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     else:
         du, db1 = ops.linear_dgrad(dt, p["mlp.fc2.weight"], dgelu_preact=s["u"], want_colsum=True)
     G["mlp.fc1.bias"].copy_(db1)
-    h2 = ops.ln_fwd(s["x1"], p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)[0] if lean else s["h2"]
+    h2 = s.pop("h2", None)
+    if h2 is None:
+        h2 = ops.ln_fwd(s["x1"], p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)[0]
     ops.linear_wgrad(du, h2, out=G["mlp.fc1.weight"])
     del h2
     dh2 = ops.linear_dgrad(du, p["mlp.fc1.weight"])
@@ -224,7 +236,7 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
         G["attn.proj.bias"].copy_(dx1_sum)
     ops.linear_wgrad(dt, s["a"], out=G["attn.proj.weight"])
     da = ops.linear_dgrad(dt, p["attn.proj.weight"])
-    if lean:
+    if s.get("P") is None:
         s["P"] = ops.attention_probs(s["qkv"], B, N, H, hd)
     if "att" in masks:
         dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True, drop_mask=masks["att"],
@@ -234,7 +246,9 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     del da
     G["attn.qkv.bias"].copy_(dbqkv)
     s["P"] = None
-    h1 = ops.ln_fwd(s["x"], p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)[0] if lean else s["h1"]
+    h1 = s.pop("h1", None)
+    if h1 is None:
+        h1 = ops.ln_fwd(s["x"], p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)[0]
     ops.linear_wgrad(dqkv, h1, out=G["attn.qkv.weight"])
     del h1
     dh1 = ops.linear_dgrad(dqkv, p["attn.qkv.weight"])

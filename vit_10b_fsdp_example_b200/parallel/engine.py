@@ -43,6 +43,11 @@ class _NullEvent:
         pass
 
 
+import os as _os
+
+EXTRAS_ENABLED = _os.environ.get("B200_CKPT_EXTRAS", "1") != "0"
+
+
 class FsdpUnit:
     """Sharded state of one FSDP unit on this rank."""
 
@@ -89,6 +94,9 @@ class FSDPViT:
         # the blocks below are checkpointed as in the reference (run_vit_training.py:171 checkpoint_module).
         # -1 = decide after the first step from the HBM that is actually free (see _auto_keep_blocks).
         self.keep_blocks = int(ckpt_keep_blocks) if grad_ckpt else 0
+        # how many of the kept blocks (counted from the top) additionally keep P / both LN outputs / gelu(u)
+        # instead of re-materialising them; filled by the automatic policy with whatever HBM is left over
+        self.keep_extras = {"P": 0, "h": 0, "g": 0}
         self.shard_on_cpu = shard_on_cpu
         self.training = True
         self.is_cuda = self.device.type == "cuda"
@@ -365,11 +373,38 @@ class FSDPViT:
         free, total = torch.cuda.mem_get_info(self.device)
         margin = int(float(os.environ.get("B200_CKPT_MARGIN_GB", "8")) * 2 ** 30) + total // 50
         k = max(0, min(len(self.units), (free - margin) // max(1, self.lean_bytes_per_block(batch))))
+        # left-over HBM: keep re-materialisable tensors too, best saving per byte first (P, LN outputs, gelu(u))
+        left = free - margin - k * self.lean_bytes_per_block(batch)
+        extras = []
+        for name, nbytes in self.extra_bytes_per_block(batch):
+            n = int(max(0, min(k, left // max(1, nbytes)))) if k == len(self.units) and EXTRAS_ENABLED else 0
+            left -= n * nbytes
+            extras.append(n)
+        vals = [k] + extras
         if self.dp_world > 1:
-            t = torch.tensor([k], dtype=torch.int64, device=self.device)
+            t = torch.tensor(vals, dtype=torch.int64, device=self.device)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            k = int(t.item())
-        return int(k)
+            vals = [int(v) for v in t.tolist()]
+        self.keep_extras = dict(zip(("P", "h", "g"), vals[1:]))
+        return int(vals[0])
+
+    def extra_bytes_per_block(self, batch: int):
+        cfg = self.cfg
+        es = torch.empty((), dtype=self.dtype).element_size()
+        unit = batch * cfg.num_patches * cfg.embed_dim * es
+        npad = (cfg.num_patches + 7) // 8 * 8
+        return (("P", batch * cfg.num_heads * cfg.num_patches * npad * es), ("h", 2 * unit),
+                ("g", int(cfg.mlp_ratio * unit)))
+
+    def _save_mode(self, i: int, keep_from: int):
+        """What block i stores in forward: False = only its input (checkpoint), True = everything
+        (--no_grad_ckpt), else the set of extras kept on top of the lean set."""
+        if not self.grad_ckpt:
+            return True
+        if i < keep_from:
+            return False
+        top = len(self.units) - 1 - i  # 0 for the top block: its activations are released first in backward
+        return frozenset(n for n, cnt in self.keep_extras.items() if top < cnt)
 
     def forward_backward(self, images: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One micro-step: loss, and this rank's (mean-reduced) shard gradients in ``unit.shard_grad``."""
@@ -406,7 +441,7 @@ class FSDPViT:
                 ckpt.append(x)
                 x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
             else:
-                x, s = vit.block_forward(ops, cfg, p, x, B, save="lean" if self.grad_ckpt else True, drop=self.drop,
+                x, s = vit.block_forward(ops, cfg, p, x, B, save=self._save_mode(i, keep_from), drop=self.drop,
                                          block_idx=i)
                 saved_all.append(s)
             if self.reshard_after_forward and i != len(blocks) - 1:
