@@ -23,7 +23,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")

@@ -7,7 +7,7 @@ Reference: ``build_datasets`` (run_vit_training.py:30-96), ``FakeImageNetDataset
 from __future__ import annotations
 
 import os
-from typing import Iterator, Optional, Tuple
+from typing import Iterator, Tuple
 
 import torch
 from torch.utils.data import DataLoader, Dataset

@@ -9,7 +9,7 @@ All matrices are 2-D ``[tokens, features]``; the model code does its own reshape
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -14,7 +14,8 @@ Both implement the same small interface used by ``engine.FSDPViT``:
 """
 from __future__ import annotations
 
-from typing import List, Optional
+import os
+from typing import Optional
 
 import torch
 import torch.distributed as dist
@@ -114,8 +115,6 @@ class Sm100Backend(TorchDistBackend):
     def __init__(self, world: int, rank: int, device: torch.device, comm_ctas: int = 24):
         super().__init__(world, rank, device)
         from ..ops import native
-
-        import os
 
         self._C = native.load()
         self.comm_ctas = int(os.environ.get("B200_COMM_CTAS", comm_ctas))  # SMs the stand-alone collectives may take

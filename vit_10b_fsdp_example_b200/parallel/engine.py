@@ -10,6 +10,8 @@ What the reference gets from ``XlaFullyShardedDataParallel`` + ``checkpoint_modu
   * backward: re-gather, recompute the block from its checkpointed input (``grad_ckpt``), run the
               hand-written backward, reduce-scatter (mean) the unit's gradients while the next block
               computes -> 2 all-gathers + 1 reduce-scatter per block per step                    (:194,357)
+  * memory-aware extension of ``grad_ckpt``: the top K blocks keep a lean activation set instead of being
+              recomputed, K sized from the HBM that is free after the first step (``ckpt_keep_blocks``)
   * ``clip_grad_norm_`` over the *full* gradient (local sum of squares -> all-reduce)           (:266-270)
   * ``--run_without_fsdp``: replicated parameters + gradient all-reduce (DDP comparison mode)   (:171-172,271-275)
   * ``--shard_on_cpu``: blocks are built, sharded on the host one at a time, only shards reach HBM (:175-178)
@@ -22,9 +24,11 @@ no cast pass.  On one GPU the gathered buffer aliases the shard itself (zero-cop
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional
 
 import torch
+import torch.distributed as dist
 
 from ..config import ViTConfig
 from ..models import vit
@@ -43,9 +47,8 @@ class _NullEvent:
         pass
 
 
-import os as _os
-
-EXTRAS_ENABLED = _os.environ.get("B200_CKPT_EXTRAS", "1") != "0"
+# keep re-materialisable tensors (P, LN outputs, gelu(u)) too when HBM is left over after keeping every block
+EXTRAS_ENABLED = os.environ.get("B200_CKPT_EXTRAS", "1") != "0"
 
 
 class FsdpUnit:
@@ -117,8 +120,6 @@ class FSDPViT:
         self._sumsq = None
         self._fused_sumsq = False
         self.step_count = 0
-        import os
-
         self.fuse_all_gather = fuse_all_gather and os.environ.get("B200_FUSE_AG", "1") != "0"
         self._unrecorded = set()  # ids of events created but never recorded (must not be waited on during capture)
         self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
@@ -363,11 +364,7 @@ class FSDPViT:
         allocator fragmentation; the result is the minimum over ranks so every GPU runs the same schedule."""
         if not self.is_cuda:
             return 0
-        import os
-
         if self.dp_world > 1:
-            import torch.distributed as dist
-
             dist.all_reduce(torch.zeros(1, device=self.device))  # communicator buffers exist before we measure
         torch.cuda.synchronize(self.device)
         free, total = torch.cuda.mem_get_info(self.device)

@@ -20,7 +20,7 @@ every parameter view is a legal TMA base address.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 ALIGN = 64  # elements
 
