@@ -237,6 +237,23 @@ def run_ours(args):
         launches = graphed.launches_per_step * args.steps
     clocks = sampler.stop() if sampler else {}
     peak_gb = torch.cuda.max_memory_allocated() / 1e9
+    exposed = None
+    if graphed is None:
+        # Secondary metric of BASELINE.json: exposed communication per step, probed outside the timed region.
+        # A rank that is ahead of its peers also waits for *them* inside these events (GPUs under a power cap run at
+        # different clocks), so the rank with the smallest stall is the critical path: its number is the exposed
+        # communication; the largest one mostly measures how unequal the GPUs are.
+        probe_steps = 2
+        with model.exposed_comm_probe() as pr:
+            for _ in range(probe_steps):
+                step_dev()
+        lo = torch.tensor([pr["ms"] / probe_steps], dtype=torch.float64, device=device)
+        hi = lo.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        exposed = {"critical_path_rank_ms": float(lo.item()), "max_over_ranks_ms": float(hi.item()),
+                   "waits_per_step": pr["waits"] // probe_steps}
     kept = max(0, model.keep_blocks)
     full_ckpt_ms = None
     if kept > 0 and graphed is None and not args.no_full_ckpt_probe:
@@ -272,6 +289,7 @@ def run_ours(args):
                        "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0),
                        "power_w_max": clocks.get("power_w_max")},
             "gpu_launches": launches,
+            "exposed_comm_ms_per_step": exposed,
             "model_tflops_per_gpu": flops / (dev_ms * 1e-3) / 1e12,
             "peak_mem_gb": peak_gb, "init_s": t_init, "loss": last_loss[0],
         }

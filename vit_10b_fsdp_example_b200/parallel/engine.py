@@ -121,6 +121,7 @@ class FSDPViT:
         self._fused_sumsq = False
         self.step_count = 0
         self.fuse_all_gather = fuse_all_gather and os.environ.get("B200_FUSE_AG", "1") != "0"
+        self._stall_probe = None  # list of (event, event) pairs while exposed_comm_probe() is active
         self._unrecorded = set()  # ids of events created but never recorded (must not be waited on during capture)
         self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
 
@@ -236,7 +237,35 @@ class FSDPViT:
 
     def _wait(self, ev):
         if self.is_cuda and ev is not None and id(ev) not in self._unrecorded:
-            torch.cuda.current_stream().wait_event(ev)
+            cur = torch.cuda.current_stream()
+            probe = self._stall_probe is not None and cur != self.comm_stream
+            if probe:  # exposed-communication probe: how long the compute stream sits in this wait
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+            cur.wait_event(ev)
+            if probe:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(cur)
+                self._stall_probe.append((e0, e1))
+
+    @contextlib.contextmanager
+    def exposed_comm_probe(self):
+        """``with model.exposed_comm_probe() as r: <steps>`` -> r["ms"] = total time the compute stream spent
+        blocked on communication-stream events (all-gather not there yet, reduce-scatter still reading a gradient
+        buffer, end-of-step join) and r["waits"] = number of such waits.  This is BASELINE.json's secondary metric
+        "exposed comm ms/step".  Two back-to-back event records cost ~2 us themselves, so ~0.3 ms per ViT-10B step
+        is measurement floor.  The all-gather slices pulled *inside* the qkv / fc1 GEMMs do not appear here: any
+        stall there is part of that GEMM's duration."""
+        res = {"ms": 0.0, "waits": 0}
+        self._stall_probe = []
+        try:
+            yield res
+        finally:
+            pairs, self._stall_probe = self._stall_probe, None
+            if self.is_cuda:
+                torch.cuda.synchronize(self.device)
+                res["ms"] = float(sum(a.elapsed_time(b) for a, b in pairs))
+                res["waits"] = len(pairs)
 
     # ------------------------------------------------------------------------------------------------
     # gather / reduce scheduling
