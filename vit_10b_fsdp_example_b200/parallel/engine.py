@@ -127,7 +127,10 @@ class FSDPViT:
 
         # ---- streams ----
         if self.is_cuda:
-            self.comm_stream = torch.cuda.Stream(device=self.device)
+            # B200_COMM_PRIORITY=-1 puts the collectives on a high-priority stream (their CTAs are then placed
+            # ahead of pending GEMM CTAs instead of at the next kernel tail); default 0 until A/B-measured.
+            self.comm_stream = torch.cuda.Stream(device=self.device,
+                                                 priority=int(os.environ.get("B200_COMM_PRIORITY", "0")))
         else:
             self.comm_stream = None
 
