@@ -1,4 +1,4 @@
-// Host API of the fused tcgen05 attention forward (see attention_sm100.cu).
+// Host API of the fused tcgen05 attention kernels (attention_sm100.cu, attention_bwd_sm100.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -12,5 +12,13 @@ bool attention_fwd_supported(int N, int hd);
 // probs: normalised softmax [B*H, N, ldp] bf16 or null (only written when the un-fused backward needs it).
 void attention_fwd(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, __nv_bfloat16* probs,
                    int64_t ldp, int B, int N, int H, int hd, cudaStream_t stream);
+
+bool attention_bwd_supported(int N, int hd);
+
+// Fused backward (attention_bwd_sm100.cu).  dout / out: [B*N, H*hd] gradient and forward output of the attention core,
+// lse: [B*H, N] from attention_fwd, delta: [B*H, N] fp32 workspace (written here), dqkv: packed [B*N, 3*H*hd].
+void attention_bwd(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16* dout, int64_t ld_do,
+                   const __nv_bfloat16* out, int64_t ld_o, const float* lse, float* delta, __nv_bfloat16* dqkv,
+                   int B, int N, int H, int hd, cudaStream_t stream);
 
 }  // namespace b200

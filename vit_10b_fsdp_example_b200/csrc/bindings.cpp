@@ -109,6 +109,20 @@ void attention_fwd(Tensor qkv, Tensor out, OptT lse, OptT probs, int64_t B, int6
                         (int)N, (int)H, (int)hd, cur_stream());
 }
 
+bool attention_bwd_supported(int64_t N, int64_t hd) { return b200::attention_bwd_supported((int)N, (int)hd); }
+
+void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta, Tensor dqkv, int64_t B, int64_t N,
+                   int64_t H, int64_t hd) {
+    c10::cuda::CUDAGuard guard(qkv.device());
+    TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && dout.stride(1) == 1 && out.stride(1) == 1 &&
+                    dqkv.is_contiguous() && lse.is_contiguous() && delta.is_contiguous(),
+                "attention_bwd: bad layouts");
+    TORCH_CHECK(lse.numel() == B * H * N && delta.numel() == B * H * N && dqkv.size(1) == 3 * H * hd,
+                "attention_bwd: bad shapes");
+    b200::attention_bwd(bf16_ptr(qkv), qkv.stride(0), bf16_ptr(dout), dout.stride(0), bf16_ptr(out), out.stride(0),
+                        f32_ptr(lse), f32_ptr(delta), bf16_mut(dqkv), (int)B, (int)N, (int)H, (int)hd, cur_stream());
+}
+
 void cross_entropy(Tensor logits, Tensor target, OptT dlogits, Tensor loss, OptT correct) {
     c10::cuda::CUDAGuard guard(logits.device());
     TORCH_CHECK(target.scalar_type() == at::kLong && target.is_cuda(), "target must be a CUDA int64 tensor");
@@ -263,6 +277,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("softmax_bwd", &softmax_bwd);
     m.def("attention_fwd", &attention_fwd);
     m.def("attention_fwd_supported", &attention_fwd_supported);
+    m.def("attention_bwd", &attention_bwd);
+    m.def("attention_bwd_supported", &attention_bwd_supported);
     m.def("cross_entropy", &cross_entropy);
     m.def("im2col", &im2col);
     m.def("gelu_fwd", &gelu_fwd);

@@ -147,9 +147,13 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
     h1, m1, r1 = ops.ln_fwd(x, p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)
     qkv = ops.linear_fwd(h1, p["attn.qkv.weight"], p["attn.qkv.bias"], ag=ag.get("attn.qkv.weight"))
     masks = {}
+    lse = None
     if use_drop and pa > 0:
         masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
         a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
+    elif do_save and getattr(ops, "FLASH_ATTENTION", False) and ops.flash_supported(N, hd):
+        a, lse = ops.attention_fwd_lse(qkv, B, N, H, hd)  # backward rebuilds P from the row log-sum-exp
+        P = None
     else:
         a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p="P" in extras)
     if use_drop and pm > 0:
@@ -175,8 +179,8 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
         y = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"], residual=x1)
     if not do_save:
         return y, None
-    saved = dict(x=x, m1=m1, r1=r1, qkv=qkv, a=a, x1=x1, m2=m2, r2=r2, u=u, masks=masks)
-    if "P" in extras:
+    saved = dict(x=x, m1=m1, r1=r1, qkv=qkv, a=a, x1=x1, m2=m2, r2=r2, u=u, masks=masks, lse=lse)
+    if "P" in extras and lse is None:
         saved["P"] = P
     if "h" in extras:
         saved["h1"], saved["h2"] = h1, h2
@@ -236,13 +240,16 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
         G["attn.proj.bias"].copy_(dx1_sum)
     ops.linear_wgrad(dt, s["a"], out=G["attn.proj.weight"])
     da = ops.linear_dgrad(dt, p["attn.proj.weight"])
-    if s.get("P") is None:
-        s["P"] = ops.attention_probs(s["qkv"], B, N, H, hd)
-    if "att" in masks:
-        dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True, drop_mask=masks["att"],
-                                        drop_scale=1.0 / (1.0 - pa))
+    if s.get("lse") is not None:  # flash-style: P is rebuilt inside the fused backward kernels
+        dqkv, dbqkv = ops.attention_bwd_lse(da, s["qkv"], s["a"], s["lse"], B, N, H, hd, want_colsum=True)
     else:
-        dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True)
+        if s.get("P") is None:
+            s["P"] = ops.attention_probs(s["qkv"], B, N, H, hd)
+        if "att" in masks:
+            dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True,
+                                            drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
+        else:
+            dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True)
     del da
     G["attn.qkv.bias"].copy_(dbqkv)
     s["P"] = None

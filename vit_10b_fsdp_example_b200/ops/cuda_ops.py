@@ -235,6 +235,29 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
     return out, p
 
 
+# Fused (flash-style) forward + backward pair: forward keeps the log-sum-exp, csrc/attention_bwd_sm100.cu rebuilds P.
+# NOT yet validated on hardware (written after the round-1 GPU budget was spent): opt in with B200_FUSED_ATTN_BWD=1.
+FLASH_ATTENTION = _os.environ.get("B200_FUSED_ATTN_BWD", "0") == "1"
+
+
+def flash_supported(N: int, hd: int) -> bool:
+    return bool(_C.attention_fwd_supported(N, hd) and _C.attention_bwd_supported(N, hd))
+
+
+def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
+    out = torch.empty(B * N, H * hd, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
+    _C.attention_fwd(qkv, out, lse, None, B, N, H, hd)
+    return out, lse
+
+
+def attention_bwd_lse(dout, qkv, out, lse, B: int, N: int, H: int, hd: int, want_colsum: bool = False):
+    dqkv = torch.empty(B * N, 3 * H * hd, dtype=qkv.dtype, device=qkv.device)
+    delta = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
+    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd)
+    return (dqkv, colsum(dqkv)) if want_colsum else dqkv
+
+
 def attention_probs(qkv, B: int, N: int, H: int, hd: int):
     """P = softmax(Q K^T / sqrt(hd)) alone: re-materialised in backward for blocks that kept only qkv."""
     D = H * hd

@@ -128,6 +128,40 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
     return o, p
 
 
+# Flash-style pair: the forward keeps only the log-sum-exp of every score row, the backward rebuilds P from it
+# (csrc/attention_bwd_sm100.cu on the GPU).  Off by default; tests flip FLASH_ATTENTION to exercise the model path.
+FLASH_ATTENTION = False
+
+
+def flash_supported(N: int, hd: int) -> bool:
+    return True
+
+
+def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
+    D = H * hd
+    q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    lse = torch.logsumexp(s, dim=-1)  # [B, H, N]
+    o = (torch.exp(s - lse[..., None]) @ v).permute(0, 2, 1, 3).reshape(B * N, D).to(qkv.dtype)
+    return o, lse.reshape(B * H, N).contiguous()
+
+
+def attention_bwd_lse(dout, qkv, out, lse, B: int, N: int, H: int, hd: int, want_colsum: bool = False):
+    D = H * hd
+    q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    do = _f32(dout).view(B, N, H, hd).permute(0, 2, 1, 3)
+    o = _f32(out).view(B, N, H, hd).permute(0, 2, 1, 3)
+    p = torch.exp((q @ k.transpose(-1, -2)) * (hd ** -0.5) - lse.view(B, H, N, 1))
+    delta = (do * o).sum(dim=-1, keepdim=True)
+    dv = p.transpose(-1, -2) @ do
+    ds = (hd ** -0.5) * p * (do @ v.transpose(-1, -2) - delta)
+    dq = ds @ k
+    dk = ds.transpose(-1, -2) @ q
+    dqkv = torch.stack([dq, dk, dv], dim=0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D).to(qkv.dtype)
+    cs = _f32(dqkv).sum(dim=0) if want_colsum else None
+    return (dqkv, cs) if want_colsum else dqkv
+
+
 def attention_probs(qkv, B: int, N: int, H: int, hd: int):
     """P alone (re-materialised in backward when only qkv was kept)."""
     q, k, _ = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
