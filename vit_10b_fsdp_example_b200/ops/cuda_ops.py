@@ -236,7 +236,10 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
 
 
 # Fused (flash-style) forward + backward pair: forward keeps the log-sum-exp, csrc/attention_bwd_sm100.cu rebuilds P.
-# NOT yet validated on hardware (written after the round-1 GPU budget was spent): opt in with B200_FUSED_ATTN_BWD=1.
+# Kernel numerics are validated on B200 (tests/test_gpu_attention.py::test_fused_attention_backward) and the pair is
+# 1.75x faster than GEMMs + softmax kernels at ViT-L shapes (404 vs 706 us incl. P re-materialisation) but not yet at
+# hd = 160 (1833 vs 1783 us: one CTA per SM, nothing overlaps its load / epilogue phases).  The model-level switch
+# stays opt-in (B200_FUSED_ATTN_BWD=1) until the engine path has been run on hardware too.
 FLASH_ATTENTION = _os.environ.get("B200_FUSED_ATTN_BWD", "0") == "1"
 
 
