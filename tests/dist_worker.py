@@ -22,6 +22,10 @@ def run(rank, world, port, opts, out_path):
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
+    if opts.get("poison"):  # NaN-fill every gathered-parameter buffer on release: catches use-after-reshard
+        from vit_10b_fsdp_example_b200.parallel import engine as _engine
+
+        _engine.DEBUG_POISON = True
     cfg = tiny_cfg(**opts.get("model", {}))
     model = FSDPViT(cfg, world=world, rank=rank, dtype=torch.float32,
                     reshard_after_forward=opts.get("reshard", True), flatten_parameters=opts.get("flatten", False),

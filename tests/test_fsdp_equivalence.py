@@ -26,6 +26,8 @@ def baseline(tmp_path_factory):
     (2, {"reshard": False}),
     (2, {"grad_ckpt": False}),
     (2, {"keep_blocks": 1}),
+    (2, {"poison": True}),
+    (2, {"poison": True, "grad_ckpt": False, "reshard": False}),
     (2, {"shard_on_cpu": True, "flatten": True, "grad_ckpt": False, "reshard": False}),
     (2, {"no_fsdp": True}),
     (4, {}),

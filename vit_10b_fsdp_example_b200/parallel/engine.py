@@ -47,6 +47,12 @@ class _NullEvent:
         pass
 
 
+# debug aid: overwrite a gathered-parameter buffer with NaN the moment the engine releases it, so any
+# use-after-release of resharded parameters shows up as a NaN loss instead of silently reading stale weights
+DEBUG_POISON = os.environ.get("B200_DEBUG_POISON", "0") == "1"
+# NVTX ranges around every block's forward / backward (visible in nsys / ncu timelines)
+NVTX = os.environ.get("B200_NVTX", "0") == "1"
+
 # keep re-materialisable tensors (P, LN outputs, gelu(u)) too when HBM is left over after keeping every block
 EXTRAS_ENABLED = os.environ.get("B200_CKPT_EXTRAS", "1") != "0"
 
@@ -226,6 +232,17 @@ class FSDPViT:
     # ------------------------------------------------------------------------------------------------
     # stream helpers (no-ops on CPU)
     # ------------------------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def _range(self, name: str):
+        if NVTX and self.is_cuda:
+            torch.cuda.nvtx.range_push(name)
+            try:
+                yield
+            finally:
+                torch.cuda.nvtx.range_pop()
+        else:
+            yield
+
     def _new_event(self):
         return torch.cuda.Event() if self.is_cuda else _NullEvent()
 
@@ -317,6 +334,8 @@ class FSDPViT:
         """Compute is done with the gathered parameters of this unit (reshard)."""
         if self._alias or unit is self.root:
             return
+        if DEBUG_POISON and unit.full is not None:
+            unit.full.fill_(float("nan"))
         self._record(self._param_buf_free[self._param_buf_index(unit)])
         unit.full = None
         unit.gather_event = None
@@ -466,13 +485,14 @@ class FSDPViT:
                 self._issue_gather(blocks[i + 1], fuse=True)
             self._wait_gather(u)
             p = self._views(u)
-            if i < keep_from:
-                ckpt.append(x)
-                x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
-            else:
-                x, s = vit.block_forward(ops, cfg, p, x, B, save=self._save_mode(i, keep_from), drop=self.drop,
-                                         block_idx=i)
-                saved_all.append(s)
+            with self._range(f"fwd block {i}"):
+                if i < keep_from:
+                    ckpt.append(x)
+                    x, _ = vit.block_forward(ops, cfg, p, x, B, save=False, drop=self.drop, block_idx=i)
+                else:
+                    x, s = vit.block_forward(ops, cfg, p, x, B, save=self._save_mode(i, keep_from), drop=self.drop,
+                                             block_idx=i)
+                    saved_all.append(s)
             if self.reshard_after_forward and i != len(blocks) - 1:
                 self._release_params(u)  # the last block is needed again immediately by backward
         logits, head_saved = vit.head_forward(ops, cfg, rp, x, B)
@@ -489,14 +509,15 @@ class FSDPViT:
                 self._issue_gather(blocks[i - 1], fuse=i - 1 < keep_from)  # prefetch for the backward sweep
             self._wait_gather(u)
             p = self._views(u)
-            if i < keep_from:
-                xin = ckpt.pop()
-                _, s = vit.block_forward(ops, cfg, p, xin, B, save=True, drop=self.drop, block_idx=i)
-            else:
-                s = saved_all.pop()
-            g = self._grad_views(u)
-            dx, dx_sum = vit.block_backward(ops, cfg, p, g, s, dx, dx_sum, B)
-            del s
+            with self._range(f"bwd block {i}"):
+                if i < keep_from:
+                    xin = ckpt.pop()
+                    _, s = vit.block_forward(ops, cfg, p, xin, B, save=True, drop=self.drop, block_idx=i)
+                else:
+                    s = saved_all.pop()
+                g = self._grad_views(u)
+                dx, dx_sum = vit.block_backward(ops, cfg, p, g, s, dx, dx_sum, B)
+                del s
             self._release_params(u)
             self._issue_reduce(u)
         vit.stem_backward(ops, cfg, rp, rg, stem_saved, dx, dx_sum)
