@@ -13,6 +13,11 @@ bool attention_fwd_supported(int N, int hd);
 void attention_fwd(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, __nv_bfloat16* probs,
                    int64_t ldp, int B, int N, int H, int hd, cudaStream_t stream);
 
+// Long-sequence forward (any even N; two passes over 64-key tiles, attention_bwd_sm100.cu): out + row log-sum-exp.
+bool attention_fwd_long_supported(int N, int hd);
+void attention_fwd_long(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, int B, int N, int H,
+                        int hd, cudaStream_t stream);
+
 bool attention_bwd_supported(int N, int hd);
 
 // Fused backward (attention_bwd_sm100.cu).  dout / out: [B*N, H*hd] gradient and forward output of the attention core,

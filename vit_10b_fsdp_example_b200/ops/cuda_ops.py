@@ -243,14 +243,24 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
 FLASH_ATTENTION = _os.environ.get("B200_FUSED_ATTN_BWD", "0") == "1"
 
 
+# N > 256 (336 px: 576 tokens) goes through the two-pass long-sequence forward; that kernel and the N > 256 use of the
+# backward kernels have not run on hardware yet (B200_FUSED_ATTN_LONG=1 to try them).
+FLASH_LONG = _os.environ.get("B200_FUSED_ATTN_LONG", "0") == "1"
+
+
 def flash_supported(N: int, hd: int) -> bool:
-    return bool(_C.attention_fwd_supported(N, hd) and _C.attention_bwd_supported(N, hd))
+    if N <= 256:
+        return bool(_C.attention_fwd_supported(N, hd) and _C.attention_bwd_supported(N, hd))
+    return bool(FLASH_LONG and _C.attention_fwd_long_supported(N, hd) and _C.attention_bwd_supported(N, hd))
 
 
 def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
     out = torch.empty(B * N, H * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    _C.attention_fwd(qkv, out, lse, None, B, N, H, hd)
+    if N <= 256:
+        _C.attention_fwd(qkv, out, lse, None, B, N, H, hd)
+    else:
+        _C.attention_fwd_long(qkv, out, lse, B, N, H, hd)
     return out, lse
 
 
