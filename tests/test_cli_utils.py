@@ -79,3 +79,35 @@ def test_fake_data_pipeline():
     assert len(train_loader) == (1281167 // 2) // 4
     data, target = next(iter(train_loader))
     assert data.shape == (4, 3, 32, 32) and target.shape == (4,) and int(target.sum()) == 0
+
+
+def test_image_folder_pipeline(tmp_path):
+    """Real-data path (reference run_vit_training.py:39-56,62-88): ImageFolder(train/val) + the reference's transforms,
+    DistributedSampler (drop_last) and a DataLoader, on a generated 2-class image tree."""
+    from PIL import Image
+
+    rng = torch.Generator().manual_seed(0)
+    for split, per_class in (("train", 6), ("val", 4)):
+        for cls in ("n01", "n02"):
+            d = tmp_path / split / cls
+            d.mkdir(parents=True)
+            for i in range(per_class):
+                arr = (torch.rand(40, 52, 3, generator=rng) * 255).to(torch.uint8).numpy()
+                Image.fromarray(arr).save(d / f"img_{i}.jpeg")
+    cfg = parse_args(["--data_dir", str(tmp_path), "--image_size", "32", "--batch_size", "4", "--num_workers", "0"])
+    logs = []
+    train_ds, train_loader, train_sampler, val_ds, val_loader, val_sampler = build_datasets(
+        cfg, torch.device("cpu"), 2, 0, log=logs.append)
+    assert "loading images from directory" in logs[0]
+    assert len(train_ds) == 12 and len(val_ds) == 8
+    assert len(train_sampler) == 6 and len(val_sampler) == 4  # this rank's half
+    train_sampler.set_epoch(1)
+    batches = list(train_loader)
+    assert len(batches) == 3  # 6 samples / local batch 2, drop_last
+    data, target = batches[0]
+    assert data.shape == (2, 3, 32, 32) and data.dtype == torch.float32 and target.dtype == torch.long
+    assert set(int(t) for b in batches for t in b[1]) <= {0, 1}
+    vdata, _ = next(iter(val_loader))
+    assert vdata.shape == (2, 3, 32, 32)
+    # Normalize() was applied: values are not confined to [0, 1]
+    assert float(data.min()) < 0.0
