@@ -422,7 +422,8 @@ class FSDPViT:
         margin = int(float(os.environ.get("B200_CKPT_MARGIN_GB", "8")) * 2 ** 30) + total // 50
         k = max(0, min(len(self.units), (free - margin) // max(1, self.lean_bytes_per_block(batch))))
         # left-over HBM: keep re-materialisable tensors too, best saving per byte first (P, LN outputs, gelu(u))
-        left = free - margin - k * self.lean_bytes_per_block(batch)
+        # (only 60 % of it: the extras change the allocation pattern, keep slack for allocator fragmentation)
+        left = int(0.6 * (free - margin - k * self.lean_bytes_per_block(batch)))
         extras = []
         for name, nbytes in self.extra_bytes_per_block(batch):
             n = int(max(0, min(k, left // max(1, nbytes)))) if k == len(self.units) and EXTRAS_ENABLED else 0
