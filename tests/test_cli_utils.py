@@ -111,3 +111,21 @@ def test_image_folder_pipeline(tmp_path):
     assert vdata.shape == (2, 3, 32, 32)
     # Normalize() was applied: values are not confined to [0, 1]
     assert float(data.min()) < 0.0
+
+
+def test_backend_resolution(monkeypatch):
+    from vit_10b_fsdp_example_b200.train import resolve_backend
+
+    cuda, cpu = torch.device("cuda"), torch.device("cpu")
+    auto = parse_args(["--fake_data"])
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert resolve_backend(auto, cuda) == "sm100" and resolve_backend(auto, cpu) == "torchdist"
+    # a job that spans hosts cannot use the symmetric-memory kernels: fall back to NCCL, refuse an explicit sm100
+    monkeypatch.setenv("WORLD_SIZE", "16")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert resolve_backend(auto, cuda) == "torchdist"
+    import pytest
+    with pytest.raises(ValueError):
+        resolve_backend(parse_args(["--backend", "sm100"]), cuda)
+    assert resolve_backend(parse_args(["--backend", "nccl"]), cuda) == "torchdist"

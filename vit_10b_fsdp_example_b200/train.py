@@ -24,9 +24,22 @@ def resolve_dtype(cfg, device: torch.device) -> torch.dtype:
     return torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
 
 
+def spans_multiple_hosts() -> bool:
+    """True when a torchrun job has more ranks than this host has processes (the reference's pod launch,
+    README.md:99-101).  The symmetric-memory kernels need every peer on the same NVSwitch domain."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    return world > local
+
+
 def resolve_backend(cfg, device: torch.device) -> str:
     if cfg.backend == "auto":
-        return "sm100" if device.type == "cuda" else "torchdist"
+        if device.type != "cuda":
+            return "torchdist"
+        # one NVSwitch box: hand-written P2P / NVLS kernels; several hosts: NCCL collectives (torch.distributed)
+        return "torchdist" if spans_multiple_hosts() else "sm100"
+    if cfg.backend == "sm100" and spans_multiple_hosts():
+        raise ValueError("--backend sm100 needs all ranks on one NVLink/NVSwitch box; use --backend nccl across hosts")
     return "sm100" if cfg.backend == "sm100" else "torchdist"
 
 
