@@ -129,3 +129,22 @@ def test_backend_resolution(monkeypatch):
     with pytest.raises(ValueError):
         resolve_backend(parse_args(["--backend", "sm100"]), cuda)
     assert resolve_backend(parse_args(["--backend", "nccl"]), cuda) == "torchdist"
+
+
+def test_pod_launcher_builds_per_host_commands(capsys):
+    """Multi-host fan-out (role of xla_dist in the reference README): node ranks, rendezvous endpoint, env forwarding."""
+    from vit_10b_fsdp_example_b200 import pod_launch
+
+    rc = pod_launch.main(["--hosts", "gpu-a,gpu-b", "--nproc-per-node", "8", "--env", "NCCL_DEBUG=WARN", "--env",
+                          "FOO=a b", "--workdir", "/srv/vit", "--restart", "--dry-run", "--", "run_vit_training.py",
+                          "--fake_data", "--batch_size", "1024"])
+    assert rc == 0
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert len(lines) == 4 and lines[0].startswith("[gpu-a] if [ -f ")
+    a, b = lines[1], lines[3]
+    for ln, rank in ((a, 0), (b, 1)):
+        assert f"--node-rank={rank}" in ln and "--nnodes=2" in ln and "--nproc-per-node=8" in ln
+        assert "--master-addr=gpu-a" in ln and "--master-port=29500" in ln
+        assert "NCCL_DEBUG=WARN" in ln and "FOO='a b'" in ln and "cd /srv/vit" in ln
+        assert ln.endswith("run_vit_training.py --fake_data --batch_size 1024")
+    assert "pkill" not in a and "killall" not in a  # restarts stop the recorded PID, never a pattern
