@@ -53,3 +53,30 @@ def test_consolidation_matches_unsharded(tmp_path):
             assert torch.equal(got.reshape(-1), v.reshape(-1)), k
         saved = torch.load(prefix + "_full.pth", weights_only=False)
         assert set(saved["model"].keys()) == set(full.keys())
+
+
+def test_consolidated_checkpoint_round_trip(tmp_path):
+    """Sharded files written at world size 4 -> offline consolidation -> (a) a plain nn.Module ViT loads the result
+    with strict=True and computes the same logits as the engine, (b) the engine itself restarts from it at a
+    *different* world size (1), which the per-rank shard files alone cannot do."""
+    from vit_10b_fsdp_example_b200.models.plain import PlainViT
+
+    d = str(tmp_path)
+    prefix = os.path.join(d, "epoch_1")
+    launch(4, {"steps": 0, "seed": 7, "dump_state": prefix + "_rank_{rank}.ckpt"}, os.path.join(d, "r.json"))
+    consolidate_files(prefix, save_path=prefix + "_full.pth")
+    cfg = tiny_cfg()
+    ref = FSDPViT(cfg, dtype=torch.float32, seed=7)          # what the 4 ranks jointly hold
+    other = FSDPViT(cfg, dtype=torch.float32, seed=99)       # different init, then restored from the full file
+    full = torch.load(prefix + "_full.pth", weights_only=False)["model"]
+    other.load_full_state_dict(full)
+    a, b = full_params_of(ref), full_params_of(other)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+    plain = PlainViT.from_consolidated(prefix + "_full.pth", cfg).eval()
+    images = torch.randn(3, 3, cfg.image_size, cfg.image_size)
+    with torch.no_grad():
+        want = plain(images)
+    got = ref.eval()(images)
+    assert torch.allclose(got, want, atol=1e-4), (got - want).abs().max()

@@ -610,6 +610,26 @@ class FSDPViT:
             self._install_master(u, m.to(self.device))
         self.backend.params_updated()
 
+    def load_full_state_dict(self, full: Dict[str, torch.Tensor]) -> None:
+        """Initialise this rank's shards from a *consolidated* (unsharded, timm-style) state_dict, e.g. the output
+        of ``consolidate_sharded_ckpts``: the way to continue a run on a different number of GPUs, which per-rank
+        shard files alone cannot do (``load_state_dict`` asserts the world size is unchanged)."""
+        for u in self.all_units:
+            lay = u.layout
+            prefix = "" if u is self.root else u.name + "."
+            buf = torch.zeros(lay.full_numel, dtype=torch.float32)
+            for p in lay.params:
+                t = full[prefix + p.name].detach().to(torch.float32).cpu()
+                if p.name == "patch_embed.proj.weight":  # [D, 3, P, P] -> [D, 3*P*P] zero-padded to the TMA-legal K
+                    t = t.reshape(p.shape[0], -1)
+                    t = torch.nn.functional.pad(t, (0, p.shape[1] - t.shape[1]))
+                assert t.numel() == p.numel, f"{prefix + p.name}: {tuple(t.shape)} does not match {p.shape}"
+                buf[p.full_offset: p.full_offset + p.numel].copy_(t.reshape(-1))
+            shard = torch.zeros(lay.shard_numel, dtype=torch.float32)
+            lay.shard_from_full(buf, self.shard_rank, shard)
+            self._install_master(u, shard.to(self.device))
+        self.backend.params_updated()
+
     def get_shard_metadata(self) -> dict:
         """Everything the offline consolidation tool needs to rebuild full tensors (reference utils.py:29)."""
         return {
