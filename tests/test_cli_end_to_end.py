@@ -45,3 +45,10 @@ def test_train_resume_consolidate_via_cli(tmp_path):
     sd = sd.get("model", sd)
     assert sd["blocks.0.attn.qkv.weight"].shape == (96, 32)
     assert sd["pos_embed"].shape == (1, 16, 32) and sd["head.weight"].shape == (10, 32)
+
+    # continue on ONE process from the consolidated file (different world size than the run that wrote the shards)
+    one = [a if a != "2" or TINY[i - 1] != "--nproc" else "1" for i, a in enumerate(TINY)]
+    r4 = _run(["run_vit_training.py", *one, "--ckpt_dir", str(tmp_path / "ckpt1"), "--num_epochs", "1",
+               "--init_from_full_ckpt", full])
+    assert r4.returncode == 0, r4.stdout[-2000:] + r4.stderr[-2000:]
+    assert "parameters initialised from the consolidated checkpoint" in r4.stdout and "training completed" in r4.stdout

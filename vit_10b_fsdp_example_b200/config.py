@@ -44,6 +44,10 @@ def build_arg_parser() -> argparse.ArgumentParser:
     parser.add_argument("--run_without_fsdp", action="store_true", dest="run_without_fsdp")
     parser.add_argument("--shard_on_cpu", action="store_true", dest="shard_on_cpu")
     # ---- B200 extras (not in the reference; defaults keep reference semantics) ----
+    parser.add_argument("--init_from_full_ckpt", type=str, default="",
+                        help="initialise the parameters from a consolidated (unsharded) checkpoint written by "
+                             "consolidate_sharded_ckpts: continues a run on a different number of GPUs "
+                             "(optimizer state starts fresh; --resume_epoch restores everything but needs the same world size)")
     parser.add_argument("--ckpt_keep_blocks", type=int, default=-1,
                         help="with --grad_ckpt: how many (top) blocks keep a lean activation set instead of being "
                              "recomputed in backward; -1 = as many as the free HBM allows (measured after step 1), "

@@ -123,6 +123,11 @@ def train(rt: Runtime, cfg):
     rt.rendezvous("loaded optimizer")
     rt.master_print(f"\n=== optimizer ===\n{pprint.pformat(optimizer)}\n")
 
+    if getattr(cfg, "init_from_full_ckpt", ""):
+        full = torch.load(cfg.init_from_full_ckpt, map_location="cpu", weights_only=False)
+        model.load_full_state_dict(full.get("model", full))
+        rt.master_print(f"parameters initialised from the consolidated checkpoint {cfg.init_from_full_ckpt}")
+        del full
     # resume (each rank loads its own shard file)
     os.makedirs(cfg.ckpt_dir, exist_ok=True)
     if cfg.resume_epoch > 0:
