@@ -6,6 +6,9 @@
         bench.py --gpus 8 --steps 5 --warmup 3
     python bench.py --impl reference ...              # the UNMODIFIED reference script on stock PyTorch
 
+The timed step is the body of the reference's training loop (run_vit_training.py:259-280): forward + loss, backward,
+clip_grad_norm_ on the full gradient, optimizer.step, lr_scheduler.step, zero_grad.
+
 Protocol: ViT-10B (embed 5120, 32 heads, 32 blocks, MLP 4x, patch 14, 224 px), bf16 compute,
 `--fake_data` zeros, random-init weights, FSDP ZeRO-3 + activation checkpointing + grad clipping + AdamW +
 warmup-cosine -- the full training step of the reference.  Weak scaling: 128 images per GPU (= the

@@ -1,4 +1,5 @@
 // Host API of the sm_100a tcgen05 GEMM (see gemm_sm100.cu).
+// Every nn.Linear / conv-as-GEMM / attention matmul of the reference model (run_vit_training.py:124-153 via timm) runs on it.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -8,6 +8,14 @@ Every function launches hand-written kernels from ``_C.so``:
     4-D TMA tensor maps + a fused scale/softmax kernel (fwd) and softmax-backward kernel (bwd).
   * LayerNorm fwd/bwd, cross-entropy, im2col, column sums, sum of squares, fused AdamW.
 
+What each group replaces in the reference (all of it reached through timm / torch_xla there):
+  linear_fwd / dgrad / wgrad      nn.Linear in timm Attention.qkv / proj, Mlp.fc1 / fc2, the head (run_vit_training.py:134-141,153)
+  attention_fwd / attention_bwd   timm Attention's softmax(q k^T * hd^-0.5) v with materialised scores (:134)
+  ln_fwd / ln_bwd                 nn.LayerNorm in timm Block (eps 1e-5) and the final norm (:151, eps 1e-6)
+  patch_im2col + linear_fwd       timm PatchEmbed conv k = s = P plus the pos_embed add (:124-129,156)
+  cross_entropy                   nn.CrossEntropyLoss (:229,262) and the eval argmax/eq (:312-313)
+  adamw_* / sumsq / clip_coef     torch.optim.AdamW (:237,278) and FSDP.clip_grad_norm_ (:270)
+
 bf16 activations / weights, fp32 accumulation and statistics.  There is no PyTorch fallback here: if the
 extension is missing this module fails to import on purpose.
 """
