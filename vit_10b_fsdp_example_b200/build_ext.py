@@ -20,7 +20,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(CSRC, "build")
 SO_PATH = os.path.join(PKG_DIR, "_C.so")
 
-CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "comm.cu", "attention_sm100.cu", "attention_bwd_sm100.cu"]
+CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "comm.cu", "attention_sm100.cu", "attention_bwd_sm100.cu",
+              "attention_persist_sm100.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 
 NVCC_FLAGS = [

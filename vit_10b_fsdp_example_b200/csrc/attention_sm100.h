@@ -18,6 +18,11 @@ bool attention_fwd_long_supported(int N, int hd);
 void attention_fwd_long(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, int B, int N, int H,
                         int hd, cudaStream_t stream);
 
+// Persistent, software-pipelined forward for 128 < N <= 256 (attention_persist_sm100.cu): out, optional lse.
+bool attention_fwd_persist_supported(int N, int hd);
+void attention_fwd_persist(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, int B, int N, int H,
+                           int hd, cudaStream_t stream);
+
 bool attention_bwd_supported(int N, int hd);
 
 // Fused backward (attention_bwd_sm100.cu).  dout / out: [B*N, H*hd] gradient and forward output of the attention core,

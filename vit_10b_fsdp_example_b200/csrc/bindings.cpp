@@ -118,6 +118,17 @@ void attention_fwd_long(Tensor qkv, Tensor out, Tensor lse, int64_t B, int64_t N
                              cur_stream());
 }
 
+bool attention_fwd_persist_supported(int64_t N, int64_t hd) {
+    return b200::attention_fwd_persist_supported((int)N, (int)hd);
+}
+
+void attention_fwd_persist(Tensor qkv, Tensor out, OptT lse, int64_t B, int64_t N, int64_t H, int64_t hd) {
+    c10::cuda::CUDAGuard guard(qkv.device());
+    TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && out.is_contiguous(), "attention_fwd_persist: bad layouts");
+    b200::attention_fwd_persist(bf16_ptr(qkv), qkv.stride(0), bf16_mut(out), lse.has_value() ? f32_ptr(*lse) : nullptr,
+                                (int)B, (int)N, (int)H, (int)hd, cur_stream());
+}
+
 bool attention_bwd_supported(int64_t N, int64_t hd) { return b200::attention_bwd_supported((int)N, (int)hd); }
 
 void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta, Tensor dqkv, int64_t B, int64_t N,
@@ -287,6 +298,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("attention_fwd", &attention_fwd);
     m.def("attention_fwd_supported", &attention_fwd_supported);
     m.def("attention_fwd_long", &attention_fwd_long);
+    m.def("attention_fwd_persist", &attention_fwd_persist);
+    m.def("attention_fwd_persist_supported", &attention_fwd_persist_supported);
     m.def("attention_bwd", &attention_bwd);
     m.def("attention_bwd_supported", &attention_bwd_supported);
     m.def("cross_entropy", &cross_entropy);

@@ -207,6 +207,11 @@ FUSED_ATTENTION = _os.environ.get("B200_FUSED_ATTN", "1") != "0"
 FUSED_ATTENTION_HD160 = _os.environ.get("B200_FUSED_ATTN_HD160", "0") == "1"
 
 
+# Persistent, software-pipelined forward (csrc/attention_persist_sm100.cu): written for the hd = 160 case where the
+# one-shot kernel cannot hide its loads; not run on hardware yet -> opt in with B200_ATTN_PERSIST=1.
+ATTN_PERSIST = _os.environ.get("B200_ATTN_PERSIST", "0") == "1"
+
+
 def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0, need_p: bool = True):
     """Returns (out [B*N, D], P).  P = softmax probabilities [B*H, N, ldp] for the backward, or None when
     need_p=False and the fused kernel ran (scores never reach HBM then)."""
@@ -214,6 +219,10 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
         return torch_ops.attention_fwd(qkv, B, N, H, hd, drop_mask, drop_scale)
     D = H * hd
     ldp = _pad8(N)
+    if ATTN_PERSIST and not need_p and _C.attention_fwd_persist_supported(N, hd):
+        out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
+        _C.attention_fwd_persist(qkv, out, None, B, N, H, hd)
+        return out, None
     # hd <= 128: two CTAs fit an SM and the fused kernel is ~1.8x faster than GEMM+softmax+GEMM (ViT-L: 159 vs 279 us).
     # hd = 160 (ViT-10B) needs 200 KB of smem -> one CTA per SM with nothing to overlap its loads; measured slower
     # than the batched-GEMM path (764 vs 664 us), so that shape stays on the un-fused path unless forced.
@@ -265,7 +274,9 @@ def flash_supported(N: int, hd: int) -> bool:
 def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
     out = torch.empty(B * N, H * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    if N <= 256:
+    if ATTN_PERSIST and _C.attention_fwd_persist_supported(N, hd):
+        _C.attention_fwd_persist(qkv, out, lse, B, N, H, hd)
+    elif N <= 256:
         _C.attention_fwd(qkv, out, lse, None, B, N, H, hd)
     else:
         _C.attention_fwd_long(qkv, out, lse, B, N, H, hd)
