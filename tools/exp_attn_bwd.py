@@ -17,6 +17,9 @@ for (B, N, H, hd) in ((128, 256, 32, 160), (128, 196, 16, 64)):
     _, p = co.attention_fwd(qkv, B, N, H, hd, need_p=True)
     r = dict(shape=(B, N, H, hd),
              fused_bwd_us=t(lambda: co.attention_bwd_lse(dout, qkv, out, lse, B, N, H, hd, want_colsum=True)),
+             fused_bwd_persistent_us=(setattr(co, "ATTN_PERSIST", True),
+                                      t(lambda: co.attention_bwd_lse(dout, qkv, out, lse, B, N, H, hd, want_colsum=True)),
+                                      setattr(co, "ATTN_PERSIST", False))[1] if os.environ.get("B200_TEST_UNVERIFIED") == "1" else None,
              unfused_bwd_us=t(lambda: co.attention_bwd(dout, qkv, p, B, N, H, hd, want_colsum=True)),
              probs_remat_us=t(lambda: co.attention_probs(qkv, B, N, H, hd)),
              fused_fwd_lse_us=t(lambda: co.attention_fwd_lse(qkv, B, N, H, hd)),

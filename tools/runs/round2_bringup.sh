@@ -24,7 +24,7 @@ print("one-shot fused us", t(lambda: co._C.attention_fwd(qkv, out, None, None, B
 print("un-fused us", t(lambda: co.attention_fwd(qkv, B, N, H, hd, need_p=True)))
 PY
 echo "== attention fwd/bwd timings" >> $L
-timeout 120 python tools/exp_attn_bwd.py 2>&1 | tail -4 >> $L
+B200_TEST_UNVERIFIED=1 timeout 120 python tools/exp_attn_bwd.py 2>&1 | tail -4 >> $L
 for flash in 0 1; do
   echo "== ViT-L, B200_FUSED_ATTN_BWD=$flash" >> $L
   B200_FUSED_ATTN_BWD=$flash timeout 300 python bench.py --model vitl --steps 20 --warmup 3 --no_e2e 2>&1 | tail -1 | cut -c1-400 >> $L

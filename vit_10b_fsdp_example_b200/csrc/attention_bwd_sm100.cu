@@ -750,7 +750,7 @@ bool attention_bwd_supported(int N, int hd) {
 
 void attention_bwd(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16* dout, int64_t ld_do,
                    const __nv_bfloat16* out, int64_t ld_o, const float* lse, float* delta, __nv_bfloat16* dqkv,
-                   int B, int N, int H, int hd, cudaStream_t stream) {
+                   int B, int N, int H, int hd, cudaStream_t stream, bool persist) {
     if (!attention_bwd_supported(N, hd)) throw std::runtime_error("attention_bwd: unsupported (N, head_dim)");
     const int D = H * hd;
     {
@@ -759,6 +759,10 @@ void attention_bwd(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16
                                                                                            B, N, H, hd);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) throw std::runtime_error(std::string("attention delta launch: ") + cudaGetErrorString(err));
+    }
+    if (persist) {
+        attention_bwd_persist_core(qkv, ld_qkv, dout, ld_do, lse, delta, dqkv, B, N, H, hd, stream);
+        return;
     }
     GemmOperand q, k, v, dO;
     q.ptr = qkv, k.ptr = qkv + D, v.ptr = qkv + 2 * D, dO.ptr = dout;

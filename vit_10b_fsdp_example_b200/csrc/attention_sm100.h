@@ -27,8 +27,12 @@ bool attention_bwd_supported(int N, int hd);
 
 // Fused backward (attention_bwd_sm100.cu).  dout / out: [B*N, H*hd] gradient and forward output of the attention core,
 // lse: [B*H, N] from attention_fwd, delta: [B*H, N] fp32 workspace (written here), dqkv: packed [B*N, 3*H*hd].
+// persist = true runs the persistent 8-softmax-warp variant (attention_bwd_persist_sm100.cu) instead of the one-shot kernels.
 void attention_bwd(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16* dout, int64_t ld_do,
                    const __nv_bfloat16* out, int64_t ld_o, const float* lse, float* delta, __nv_bfloat16* dqkv,
-                   int B, int N, int H, int hd, cudaStream_t stream);
+                   int B, int N, int H, int hd, cudaStream_t stream, bool persist = false);
+void attention_bwd_persist_core(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16* dout, int64_t ld_do,
+                                const float* lse, const float* delta, __nv_bfloat16* dqkv, int B, int N, int H, int hd,
+                                cudaStream_t stream);
 
 }  // namespace b200

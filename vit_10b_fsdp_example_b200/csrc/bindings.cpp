@@ -132,7 +132,7 @@ void attention_fwd_persist(Tensor qkv, Tensor out, OptT lse, int64_t B, int64_t 
 bool attention_bwd_supported(int64_t N, int64_t hd) { return b200::attention_bwd_supported((int)N, (int)hd); }
 
 void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta, Tensor dqkv, int64_t B, int64_t N,
-                   int64_t H, int64_t hd) {
+                   int64_t H, int64_t hd, bool persist) {
     c10::cuda::CUDAGuard guard(qkv.device());
     TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && dout.stride(1) == 1 && out.stride(1) == 1 &&
                     dqkv.is_contiguous() && lse.is_contiguous() && delta.is_contiguous(),
@@ -140,7 +140,8 @@ void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta
     TORCH_CHECK(lse.numel() == B * H * N && delta.numel() == B * H * N && dqkv.size(1) == 3 * H * hd,
                 "attention_bwd: bad shapes");
     b200::attention_bwd(bf16_ptr(qkv), qkv.stride(0), bf16_ptr(dout), dout.stride(0), bf16_ptr(out), out.stride(0),
-                        f32_ptr(lse), f32_ptr(delta), bf16_mut(dqkv), (int)B, (int)N, (int)H, (int)hd, cur_stream());
+                        f32_ptr(lse), f32_ptr(delta), bf16_mut(dqkv), (int)B, (int)N, (int)H, (int)hd, cur_stream(),
+                        persist);
 }
 
 void cross_entropy(Tensor logits, Tensor target, OptT dlogits, Tensor loss, OptT correct) {

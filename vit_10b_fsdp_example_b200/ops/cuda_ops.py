@@ -286,7 +286,7 @@ def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
 def attention_bwd_lse(dout, qkv, out, lse, B: int, N: int, H: int, hd: int, want_colsum: bool = False):
     dqkv = torch.empty(B * N, 3 * H * hd, dtype=qkv.dtype, device=qkv.device)
     delta = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd)
+    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd, ATTN_PERSIST)
     return (dqkv, colsum(dqkv)) if want_colsum else dqkv
 
 
