@@ -89,3 +89,13 @@ def test_flash_style_attention_path_matches_autograd(monkeypatch):
         for name, p in params.items():
             g = p.grad if p.grad is not None else torch.zeros_like(p)
             assert (got[name].double() - g).abs().max().item() / (g.abs().max().item() + 1e-8) < 2e-4, name
+
+
+def test_exposed_comm_probe_is_a_noop_on_cpu():
+    """The probe API exists on every device; without CUDA streams there is nothing to wait for."""
+    cfg = tiny_cfg()
+    model = FSDPViT(cfg, dtype=torch.float32, seed=3)
+    images = torch.randn(2, 3, cfg.image_size, cfg.image_size)
+    with model.exposed_comm_probe() as r:
+        model.forward_backward(images, torch.tensor([1, 2]))
+    assert r == {"ms": 0.0, "waits": 0} and model._stall_probe is None
