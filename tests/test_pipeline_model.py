@@ -1,0 +1,55 @@
+"""Protocol model of the warp-specialised attention kernels (tools/pipeline_model.py): every kernel's mbarrier
+pipeline is replayed under randomised completion orders and checked for deadlock, premature parity passes and
+buffer overwrites; injected faults must be caught (so the checker is known to be sensitive)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import pipeline_model as pm  # noqa: E402
+
+SEEDS = range(40)
+
+
+@pytest.mark.parametrize("nt", [1, 2, 3, 4, 9])
+@pytest.mark.parametrize("ts_bufs,kT", [(2, True), (1, True), (2, False)])
+def test_one_shot_backward_protocol(nt, ts_bufs, kT):
+    """attention_bwd_sm100.cu (validated on hardware): also calibrates the model."""
+    for seed in SEEDS:
+        pm.model_bwd(seed, 1, nt, ts_bufs, 4, kT, persistent=False)
+
+
+@pytest.mark.parametrize("n_items,nt", [(1, 4), (2, 1), (3, 3), (4, 4), (2, 9)])
+@pytest.mark.parametrize("kT", [True, False])
+def test_persistent_backward_protocol(n_items, nt, kT):
+    for seed in SEEDS:
+        pm.model_bwd(seed, n_items, nt, 2, 8, kT, persistent=True)
+
+
+@pytest.mark.parametrize("n_items,nkt", [(1, 4), (3, 4), (4, 3), (5, 1), (3, 2)])
+def test_persistent_forward_protocol(n_items, nkt):
+    for seed in SEEDS:
+        pm.model_fwd_persist(seed, n_items, nkt)
+
+
+@pytest.mark.parametrize("nt", [1, 2, 5, 9, 16])
+def test_long_forward_protocol(nt):
+    for seed in SEEDS:
+        pm.model_fwd_long(seed, nt)
+
+
+@pytest.mark.parametrize("bug,args", [
+    ("no_x_empty", dict(n_items=3, nt=4, ts_bufs=2, warps=8, kT=True, persistent=True)),
+    ("y_empty_parity", dict(n_items=3, nt=4, ts_bufs=2, warps=8, kT=True, persistent=True)),
+    ("no_e_empty", dict(n_items=1, nt=4, ts_bufs=2, warps=4, kT=True, persistent=False)),
+    ("no_ts_empty", dict(n_items=1, nt=4, ts_bufs=1, warps=4, kT=True, persistent=False)),  # single T_s buffer
+])
+def test_injected_faults_are_detected(bug, args):
+    caught = 0
+    for seed in range(60):
+        try:
+            pm.model_bwd(seed, bug=bug, **args)
+        except pm.ProtocolError:
+            caught += 1
+    assert caught > 0, f"fault {bug} was never detected"
