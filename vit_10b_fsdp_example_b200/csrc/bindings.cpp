@@ -248,31 +248,46 @@ bool make_adam(const OptT& hi, const OptT& lo, const OptT& m, const OptT& v, con
     a.inv_bc2 = 1.f / (1.f - powf(a.beta2, (float)hyper[5]));
     return true;
 }
-void p2p_reduce_scatter(std::vector<int64_t> peer_ptrs, int64_t rank, Tensor out, Tensor seg_table,
-                        int64_t total_chunks, bool in_is_bf16, double scale, OptT sumsq_out, int64_t max_ctas, OptT hi,
-                        OptT lo, OptT m, OptT v, std::vector<double> hyper) {
-    c10::cuda::CUDAGuard guard(out.device());
-    b200::AdamFuse a;
-    const bool fused = make_adam(hi, lo, m, v, hyper, a);
-    b200::p2p_reduce_scatter(peer_ptrs, (int)rank, f32_ptr(out), seg_ptr(seg_table), (int)seg_table.size(0),
-                             total_chunks, in_is_bf16, (float)scale,
-                             sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr, (int)max_ctas, cur_stream(),
-                             fused ? &a : nullptr);
-}
-void nvls_reduce_scatter(int64_t mc_ptr, int64_t rank, int64_t world, Tensor out, Tensor seg_table,
-                         int64_t total_chunks, double scale, OptT sumsq_out, int64_t max_ctas, OptT hi, OptT lo, OptT m,
-                         OptT v, std::vector<double> hyper) {
-    c10::cuda::CUDAGuard guard(out.device());
-    b200::AdamFuse a;
-    const bool fused = make_adam(hi, lo, m, v, hyper, a);
-    b200::nvls_reduce_scatter(mc_ptr, (int)rank, (int)world, f32_ptr(out), seg_ptr(seg_table), (int)seg_table.size(0),
-                              total_chunks, (float)scale, sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr,
-                              (int)max_ctas, cur_stream(), fused ? &a : nullptr);
-}
 inline uint32_t* seq_ptr(const OptT& t) {
     if (!t.has_value()) return nullptr;
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kInt, "sequence counters: CUDA int32 tensor");
     return reinterpret_cast<uint32_t*>(t->data_ptr());
+}
+// sync = [] (caller brackets with barriers) or [rank, world, slot_ready, slot_done, counter_idx] + flag_ptrs, seq_dev, cta_ctr
+bool make_sync(const std::vector<int64_t>& sync, const std::vector<int64_t>& flag_ptrs, const OptT& seq_dev,
+               const OptT& cta_ctr, b200::CommSync& cs) {
+    if (sync.empty()) return false;
+    TORCH_CHECK(sync.size() == 5 && seq_dev.has_value() && cta_ctr.has_value(), "bad collective sync arguments");
+    cs.flag_ptrs = flag_ptrs;
+    cs.rank = (int)sync[0], cs.world = (int)sync[1], cs.slot_ready = (int)sync[2], cs.slot_done = (int)sync[3];
+    cs.counter_idx = (int)sync[4];
+    cs.seq_dev = seq_ptr(seq_dev);
+    cs.cta_ctr = seq_ptr(cta_ctr);
+    return true;
+}
+void reduce_scatter(std::vector<int64_t> peer_ptrs, int64_t mc_ptr, int64_t rank, int64_t world, Tensor out,
+                    Tensor seg_table, int64_t total_chunks, bool in_is_bf16, double scale, OptT sumsq_out,
+                    int64_t max_ctas, std::vector<int64_t> sync, std::vector<int64_t> flag_ptrs, OptT seq_dev,
+                    OptT cta_ctr, OptT hi, OptT lo, OptT m, OptT v, std::vector<double> hyper) {
+    c10::cuda::CUDAGuard guard(out.device());
+    b200::AdamFuse a;
+    const bool fused = make_adam(hi, lo, m, v, hyper, a);
+    b200::CommSync cs;
+    const bool synced = make_sync(sync, flag_ptrs, seq_dev, cta_ctr, cs);
+    b200::reduce_scatter(peer_ptrs, mc_ptr, (int)rank, (int)world, f32_ptr(out), seg_ptr(seg_table),
+                         (int)seg_table.size(0), total_chunks, in_is_bf16, (float)scale,
+                         sumsq_out.has_value() ? f32_ptr(*sumsq_out) : nullptr, (int)max_ctas, cur_stream(),
+                         synced ? &cs : nullptr, fused ? &a : nullptr);
+}
+void all_reduce_mean(std::vector<int64_t> peer_ptrs, int64_t mc_ptr, int64_t rank, int64_t world, Tensor buf,
+                     int64_t max_ctas, std::vector<int64_t> sync, std::vector<int64_t> flag_ptrs, OptT seq_dev,
+                     OptT cta_ctr) {
+    c10::cuda::CUDAGuard guard(buf.device());
+    TORCH_CHECK(buf.scalar_type() == at::kBFloat16 && buf.is_contiguous(), "all_reduce_mean: contiguous bf16 buffer");
+    b200::CommSync cs;
+    TORCH_CHECK(make_sync(sync, flag_ptrs, seq_dev, cta_ctr, cs), "all_reduce_mean needs the flag protocol");
+    b200::all_reduce_mean_bf16(peer_ptrs, mc_ptr, (int)rank, (int)world, buf.numel() * 2, 1.0f / (float)world,
+                               (int)max_ctas, cur_stream(), &cs);
 }
 void signal_barrier(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, int64_t slot, int64_t seq,
                     OptT seq_dev) {
@@ -286,6 +301,7 @@ void allreduce_scalars(std::vector<int64_t> flag_ptrs, std::vector<int64_t> scra
 }
 int64_t ag_chunk_bytes() { return b200::ag_chunk_bytes(); }
 int64_t rs_chunk_elems() { return b200::rs_chunk_elems(); }
+int64_t rs_chunk_vecs() { return b200::rs_chunk_vecs(); }
 
 }  // namespace
 
@@ -315,8 +331,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("merge_fp32", &merge_fp32);
     m.def("clip_coef", &clip_coef);
     m.def("p2p_all_gather", &p2p_all_gather);
-    m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
-    m.def("nvls_reduce_scatter", &nvls_reduce_scatter);
+    m.def("reduce_scatter", &reduce_scatter);
+    m.def("all_reduce_mean", &all_reduce_mean);
+    m.def("rs_chunk_vecs", &rs_chunk_vecs);
     m.def("signal_barrier", &signal_barrier);
     m.def("allreduce_scalars", &allreduce_scalars);
     m.def("ag_chunk_bytes", &ag_chunk_bytes);

@@ -9,7 +9,7 @@ namespace b200 {
 
 // Segment tables live in device memory (int64).  Row formats:
 //   all-gather     : [src_rank, src_off_bytes, dst_off_bytes, nbytes, chunk_prefix]   (chunk = ag_chunk_bytes())
-//   reduce-scatter : [full_off_bytes, shard_off_elems, nelems, chunk_prefix]          (chunk = rs_chunk_elems())
+//   reduce-scatter : [full_off_bytes, shard_off_elems, nelems, chunk_prefix]          (chunk = rs_chunk_vecs() 16-byte vectors)
 void p2p_all_gather(const std::vector<int64_t>& peer_ptrs, int rank, void* out, const int64_t* seg_table_dev,
                     int nseg, int64_t total_chunks, int max_ctas, cudaStream_t stream);
 // Optional AdamW fused into the reduce-scatter epilogue (only legal when gradient clipping is off: the update
@@ -21,12 +21,26 @@ struct AdamFuse {
     float* v = nullptr;
     float lr = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, wd = 0.f, inv_bc1 = 1.f, inv_bc2 = 1.f;
 };
-void p2p_reduce_scatter(const std::vector<int64_t>& peer_ptrs, int rank, float* out, const int64_t* seg_table_dev,
-                        int nseg, int64_t total_chunks, bool in_is_bf16, float scale, float* sumsq_out, int max_ctas,
-                        cudaStream_t stream, const AdamFuse* adam = nullptr);
-void nvls_reduce_scatter(int64_t mc_ptr, int rank, int world, float* out, const int64_t* seg_table_dev, int nseg,
-                         int64_t total_chunks, float scale, float* sumsq_out, int max_ctas, cudaStream_t stream,
-                         const AdamFuse* adam = nullptr);
+// Cross-GPU flag protocol folded into reduce_scatter / all_reduce (no separate barrier launches): "inputs ready"
+// flags are published at kernel start, "done reading" flags by the last CTA, which also waits for every peer's.
+// seq_dev[counter_idx] counts the calls (device-resident -> CUDA-graph replayable); cta_ctr is a zeroed device word.
+struct CommSync {
+    std::vector<int64_t> flag_ptrs;  // every rank's symmetric flag region
+    int rank = 0, world = 1;
+    int slot_ready = 0, slot_done = 0;
+    uint32_t* seq_dev = nullptr;
+    int counter_idx = 0;
+    uint32_t* cta_ctr = nullptr;
+};
+// mc_ptr != 0: in-switch reduction (multimem.ld_reduce, bf16 only); otherwise pulls over peer_ptrs.
+// sync == nullptr: the caller brackets the call with signal_barrier()s itself.
+void reduce_scatter(const std::vector<int64_t>& peer_ptrs, int64_t mc_ptr, int rank, int world, float* out,
+                    const int64_t* seg_table_dev, int nseg, int64_t total_chunks, bool in_is_bf16, float scale,
+                    float* sumsq_out, int max_ctas, cudaStream_t stream, const CommSync* sync = nullptr,
+                    const AdamFuse* adam = nullptr);
+// In-place mean over a replicated bf16 buffer at the same symmetric offset on every rank (DDP gradient all-reduce).
+void all_reduce_mean_bf16(const std::vector<int64_t>& peer_ptrs, int64_t mc_ptr, int rank, int world, int64_t nbytes,
+                          float scale, int max_ctas, cudaStream_t stream, const CommSync* sync);
 // flags: uint32 [slot][16] per rank; scratch: float [slot][16][16] per rank (both in symmetric memory)
 // seq_dev != nullptr: sequence numbers come from (and are advanced in) device memory -> CUDA-graph replayable.
 // For allreduce_scalars the flag/scratch slot is then `slot + (seq & 1)`.
@@ -37,6 +51,7 @@ void allreduce_scalars(const std::vector<int64_t>& flag_ptrs, const std::vector<
                        uint32_t* seq_dev = nullptr, int counter_idx = 0);
 int64_t ag_chunk_bytes();
 int64_t rs_chunk_elems();
+int64_t rs_chunk_vecs();
 int comm_max_world();
 int comm_max_scalars();
 

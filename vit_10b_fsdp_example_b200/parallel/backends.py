@@ -112,12 +112,18 @@ class Sm100Backend(TorchDistBackend):
     name = "sm100"
     FLAG_BYTES = 64 * 1024  # flags: uint32[slot][16]; scratch floats follow at +32 KiB
 
-    def __init__(self, world: int, rank: int, device: torch.device, comm_ctas: int = 24):
+    # flag slots in the symmetric control region (uint32 [slot][16]): 0 params_updated barrier, 1-2 stand-alone
+    # barriers (tests), 4-5 scalar all-reduce, 6-7 "inputs ready" / "done reading" of reduce-scatter & all-reduce
+    SLOT_READY, SLOT_DONE, RS_COUNTER = 6, 7, 5
+
+    def __init__(self, world: int, rank: int, device: torch.device, comm_ctas: int = 64):
         super().__init__(world, rank, device)
         from ..ops import native
 
         self._C = native.load()
-        self.comm_ctas = int(os.environ.get("B200_COMM_CTAS", comm_ctas))  # SMs the stand-alone collectives may take
+        # Collective kernels are light CTAs (128 threads, <= 96 registers, no shared memory) that run NEXT TO the
+        # GEMM CTAs on the same SMs (see csrc/comm.cu); comm_ctas bounds how many SMs host one at a time.
+        self.comm_ctas = int(os.environ.get("B200_COMM_CTAS", comm_ctas))
         self.use_nvls = False
         if world == 1:  # single GPU: nothing to communicate, gathered buffers alias the shards
             return
@@ -131,6 +137,7 @@ class Sm100Backend(TorchDistBackend):
         # per-slot sequence numbers live on the device (advanced inside the kernels), so every collective launch is
         # replayable from a CUDA graph; all ranks issue the same sequence of collectives, hence identical counters
         self._seq_dev = torch.zeros(16, dtype=torch.int32, device=device)
+        self._cta_ctr = torch.zeros(1, dtype=torch.int32, device=device)  # last-CTA detection inside the collectives
         self.group_name = dist.group.WORLD.group_name
         ctrl = self._symm_alloc(self.FLAG_BYTES, torch.uint8)
         ctrl.zero_()
@@ -140,6 +147,11 @@ class Sm100Backend(TorchDistBackend):
         torch.cuda.synchronize()
         dist.barrier()
         self.use_nvls = all(v != 0 for v in self._mc.values()) and os.environ.get("B200_NVLS", "1") != "0"
+        # timing experiment only (wrong numerics): every "peer" pointer is this rank's own buffer and the barriers
+        # are skipped -> same kernels, same HBM traffic and SM footprint, but no NVLink traffic and no cross-rank waits
+        self._local_only = os.environ.get("B200_COMM_LOCAL", "0") == "1"
+        if self._local_only:
+            self.use_nvls = False
 
     # ---- symmetric allocation ----
     def _symm_alloc(self, numel: int, dtype) -> torch.Tensor:
@@ -147,6 +159,8 @@ class Sm100Backend(TorchDistBackend):
         hdl = self._symm.rendezvous(t, dist.group.WORLD)
         self._handles.append((t, hdl))
         self._peer[t.data_ptr()] = [int(p) for p in hdl.buffer_ptrs]
+        if os.environ.get("B200_COMM_LOCAL", "0") == "1":
+            self._peer[t.data_ptr()] = [int(t.data_ptr())] * self.world
         mc = 0
         try:
             if hdl.has_multicast_support:
@@ -172,6 +186,8 @@ class Sm100Backend(TorchDistBackend):
 
     def device_barrier(self, slot: int = 0) -> None:
         """Stream-ordered cross-GPU barrier on the current stream (flags in symmetric memory)."""
+        if getattr(self, "_local_only", False):
+            return
         self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, 0, self._seq_dev)
 
     # ---- segment tables (device int64), built once per (layout, purpose) ----
@@ -224,7 +240,7 @@ class Sm100Backend(TorchDistBackend):
     def _rs_table(self, layout: UnitLayout, esize: int):
         key = ("rs", id(layout), esize)
         if key not in self._seg_cache:
-            chunk = self._C.rs_chunk_elems()
+            chunk = self._C.rs_chunk_vecs() * (16 // esize)  # elements per chunk (one CTA pass of 16-byte vectors)
             rows, prefix = [], 0
             for (foff, soff, n) in layout.scatter_segments(self.rank):
                 rows.append([foff * esize, soff, n, prefix])
@@ -250,14 +266,31 @@ class Sm100Backend(TorchDistBackend):
         table, chunks = self._rs_table(layout, full_grad.element_size())
         scale = 1.0 / self.world
         a = tuple(adam) if adam is not None else (None, None, None, None, [])
-        self.device_barrier(slot=1)  # every rank's gradients for this unit are complete
-        if self.use_nvls and full_grad.dtype == torch.bfloat16:
-            self._C.nvls_reduce_scatter(self._mc[full_grad.data_ptr()], self.rank, self.world, out_shard, table,
-                                        chunks, scale, sumsq, self.comm_ctas, *a)
-        else:
-            self._C.p2p_reduce_scatter(self._peer[full_grad.data_ptr()], self.rank, out_shard, table, chunks,
-                                       full_grad.dtype == torch.bfloat16, scale, sumsq, self.comm_ctas, *a)
-        self.device_barrier(slot=2)  # every rank is done reading: the buffer may be overwritten
+        bf16 = full_grad.dtype == torch.bfloat16
+        mc = self._mc[full_grad.data_ptr()] if (self.use_nvls and bf16) else 0
+        # ONE kernel: publish "gradients complete" -> wait for the peers' -> reduce -> publish "done reading" ->
+        # wait until every peer is done (after which the gradient buffer may be overwritten)
+        self._C.reduce_scatter(self._peer[full_grad.data_ptr()], mc, self.rank, self.world, out_shard, table, chunks,
+                               bf16, scale, sumsq, self.comm_ctas, *self._sync_args(), *a)
+
+    def _sync_args(self):
+        if self._local_only:  # timing experiment: no cross-rank flags
+            return [], [], None, None
+        return ([self.rank, self.world, self.SLOT_READY, self.SLOT_DONE, self.RS_COUNTER], self._flag_ptrs,
+                self._seq_dev, self._cta_ctr)
+
+    def all_reduce_mean_(self, t: torch.Tensor) -> torch.Tensor:
+        """DDP gradient all-reduce (--run_without_fsdp; reference xm.reduce_gradients, run_vit_training.py:273) on the
+        symmetric gradient buffer: in-switch multimem.ld_reduce + multimem.st (or pull-reduce-push over peer
+        pointers), same in-kernel flag protocol as the reduce-scatter.  No NCCL."""
+        if self.world == 1:
+            return t
+        ptr = t.data_ptr()
+        if ptr not in self._peer or t.dtype != torch.bfloat16 or (t.numel() * 2) % 16 != 0 or self._local_only:
+            return super().all_reduce_mean_(t)  # not a symmetric gradient buffer: NCCL utility path
+        mc = self._mc[ptr] if self.use_nvls else 0
+        self._C.all_reduce_mean(self._peer[ptr], mc, self.rank, self.world, t, self.comm_ctas, *self._sync_args())
+        return t
 
     def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
         if self.world > 1:

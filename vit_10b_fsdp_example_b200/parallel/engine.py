@@ -390,15 +390,19 @@ class FSDPViT:
         return self
 
     def _begin_step(self) -> None:
-        """Fork the communication stream from the compute stream.  Under CUDA-graph capture this is what pulls the
-        side stream into the capture; stale cross-step events are dropped because everything of the previous step
-        has been joined back into the compute stream (and a replayed graph is ordered after the previous one)."""
+        """Fork the communication stream from the compute stream (training step AND inference pass).  Everything the
+        previous step / pass enqueued has been joined back into the compute stream -- reductions are waited for at the
+        end of forward_backward, buffer releases are recorded on the compute stream itself, the optimizer step and
+        its cross-GPU barrier run there, a replayed CUDA graph is ordered on it -- so after this fork every older
+        buffer-free event is implied and is replaced by a fresh, not-yet-recorded one.  That also keeps events recorded
+        inside a graph capture from ever being waited on by eager code (and vice versa), which CUDA rejects."""
         if not self.is_cuda or self._alias:
             return
-        if torch.cuda.is_current_stream_capturing():
-            self._param_buf_free = [self._new_event() for _ in self._param_bufs]
-            self._grad_buf_free = [self._new_event() for _ in self._grad_bufs]
-            self._unrecorded = set(id(e) for e in self._param_buf_free + self._grad_buf_free)
+        self._param_buf_free = [self._new_event() for _ in self._param_bufs]
+        self._grad_buf_free = [self._new_event() for _ in self._grad_bufs]
+        self._unrecorded = set(id(e) for e in self._param_buf_free + self._grad_buf_free)
+        for u in self.all_units:  # a gather left over from an earlier pass is stale: the shards may have changed
+            u.gather_event = None
         fork = self._record(self._new_event())
         with self._on_comm():
             self._wait(fork)
@@ -539,6 +543,7 @@ class FSDPViT:
         cfg, ops = self.cfg, self.ops
         B = images.shape[0]
         blocks = self.units
+        self._begin_step()  # the gathers below must not overtake the optimizer step / barrier on the compute stream
         self._issue_gather(self.root)
         if blocks:
             self._issue_gather(blocks[0], fuse=True)
@@ -600,7 +605,9 @@ class FSDPViT:
                 out[f"{u.name}.{g.name}"] = m[g.shard_offset: g.shard_offset + g.shard_len].clone()
         return out
 
-    def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+    def load_state_dict(self, state: Dict[str, torch.Tensor], shard_metadata: Optional[dict] = None) -> None:
+        if shard_metadata and "step_count" in shard_metadata:
+            self.step_count = int(shard_metadata["step_count"])
         for u in self.all_units:
             m = torch.empty(u.layout.shard_numel, dtype=torch.float32)
             for g in u.layout.groups:
@@ -635,6 +642,7 @@ class FSDPViT:
         return {
             "world_size": self.world, "rank": self.shard_rank, "flatten_parameters": self.flatten_parameters,
             "fsdp": self.use_fsdp, "units": [u.layout.metadata() for u in self.all_units],
+            "step_count": int(self.step_count),  # seeds the dropout masks: a resumed run must not replay epoch 1's
             "logical_shapes": {k: list(v) for k, v in vit.logical_shapes(self.cfg).items()},
             "patch_k": self.cfg.patch_k,
             "model": {k: getattr(self.cfg, k) for k in ("image_size", "patch_size", "embed_dim", "num_heads",

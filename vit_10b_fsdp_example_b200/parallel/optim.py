@@ -34,13 +34,13 @@ class ShardedAdamW:
         self.hyper = None
         if model.is_cuda and model.split_master:
             self.hyper = torch.zeros(2, dtype=torch.float32, device=model.device)
-            self._lr_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.lr_on_device = False  # True while a CUDA-graph owner keeps hyper[0] up to date itself
 
     def push_lr(self) -> None:
-        """Copy the current host learning rate into the device hyper-parameter block (async, pinned source)."""
-        self._lr_pinned[0] = float(self.param_groups[0]["lr"])
-        self.hyper[0:1].copy_(self._lr_pinned, non_blocking=True)
+        """Write the current host learning rate into the device hyper-parameter block.  The value travels as a
+        kernel argument of the fill, so every queued step sees exactly the learning rate it was enqueued with (a
+        pinned staging scalar would be re-read by copies that have not executed yet when the host runs ahead)."""
+        self.hyper[0:1].fill_(float(self.param_groups[0]["lr"]))
 
     def fused_args(self, unit):
         """Called by the engine when it enqueues the reduce-scatter of `unit` (fused mode)."""
@@ -102,4 +102,5 @@ class ShardedAdamW:
     def __repr__(self) -> str:
         g = self.param_groups[0]
         return (f"ShardedAdamW(lr={g['lr']}, betas={g['betas']}, eps={g['eps']}, weight_decay={g['weight_decay']}, "
-                f"units={len(self.model.all_units)}, fused_clip=True)")
+                f"units={len(self.model.all_units)}, clip_fused_into_update={not self.fused}, "
+                f"fused_into_reduce_scatter={self.fused})")

@@ -33,7 +33,13 @@ def save_ckpt(ckpt_path: str, model, optimizer, lr_scheduler, master_only: bool 
 def load_ckpt(ckpt_path: str, model, optimizer, lr_scheduler) -> None:
     assert os.path.exists(ckpt_path), f"checkpoint {ckpt_path} does not exist"
     ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
-    model.load_state_dict(ckpt["model"])
+    try:
+        model.load_state_dict(ckpt["model"], shard_metadata=ckpt.get("shard_metadata"))
+    except TypeError:  # a plain nn.Module-style model
+        model.load_state_dict(ckpt["model"])
     optimizer.load_state_dict(ckpt["optimizer"])
+    if getattr(model, "step_count", None) == 0 and hasattr(optimizer, "state") and hasattr(model, "all_units"):
+        # DDP checkpoints carry no shard metadata: the optimizer step count is the number of steps taken
+        model.step_count = int(optimizer.state[model.all_units[0].name]["step"])
     lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
     print(f"resumed from checkpoint {ckpt_path}\n", end="")
