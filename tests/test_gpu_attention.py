@@ -75,9 +75,6 @@ def test_fused_attention_backward(B, N, H, hd):
     _close(cs, csr, rel=5e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVERIFIED", "0") != "1",
-                    reason="long-sequence fused attention (N > 256) was written after the round-1 GPU budget was "
-                           "spent; set B200_TEST_UNVERIFIED=1 to run it (round-2 bring-up)")
 @pytest.mark.parametrize("B,N,H,hd", [(1, 320, 2, 64), (1, 576, 2, 160), (2, 576, 2, 128)])
 def test_fused_attention_long_sequence(B, N, H, hd):
     """Two-pass long-sequence forward + the fused backward at N > 256 (336 px config) vs the fp32 reference."""
@@ -98,9 +95,6 @@ def test_fused_attention_long_sequence(B, N, H, hd):
         assert err < 3e-2, f"{name}: rel err {err}"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVERIFIED", "0") != "1",
-                    reason="persistent attention forward was written after the round-1 GPU budget was spent; "
-                           "set B200_TEST_UNVERIFIED=1 to run it (round-2 bring-up)")
 @pytest.mark.parametrize("B,N,H,hd", [(2, 256, 4, 160), (3, 196, 3, 64), (5, 160, 2, 128), (40, 256, 8, 160)])
 def test_persistent_attention_forward(B, N, H, hd):
     """attention_persist_sm100.cu (one CTA per SM looping over work items) vs the fp32 reference; the last shape has
@@ -118,9 +112,6 @@ def test_persistent_attention_forward(B, N, H, hd):
     assert (lse - lser).abs().max().item() < 2e-2
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVERIFIED", "0") != "1",
-                    reason="persistent attention backward was written after the round-1 GPU budget was spent; "
-                           "set B200_TEST_UNVERIFIED=1 to run it (round-2 bring-up)")
 @pytest.mark.parametrize("B,N,H,hd", [(1, 256, 2, 64), (3, 196, 3, 64), (2, 128, 2, 128), (2, 256, 4, 160),
                                       (40, 256, 8, 160)])
 def test_persistent_attention_backward(B, N, H, hd, monkeypatch):

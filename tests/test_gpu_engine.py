@@ -143,9 +143,6 @@ def test_lean_blocks_vs_recompute(heads, dim):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_UNVERIFIED", "0") != "1",
-                    reason="engine path through the fused attention backward has not run on hardware yet "
-                           "(kernels themselves are validated in test_gpu_attention.py); round-2 bring-up")
 @pytest.mark.parametrize("heads,dim,img", [(4, 256, 112), (2, 256, 224), (2, 320, 224)])
 def test_flash_attention_engine_path(heads, dim, img, monkeypatch):
     """Same model, same data: gradients with the flash-style attention pair (lse + fused backward kernels) must
@@ -163,6 +160,7 @@ def test_flash_attention_engine_path(heads, dim, img, monkeypatch):
     res = []
     for flash in (False, True):
         monkeypatch.setattr(co, "FLASH_ATTENTION", flash)
+        monkeypatch.setattr(co, "_FLASH_ENV", "1" if flash else "0")  # force the pair on for hd = 160 too
         for keep in (0, 2):
             model = FSDPViT(cfg, device=dev, dtype=torch.bfloat16, seed=4, ckpt_keep_blocks=keep)
             loss = model.forward_backward(x, y).item()
@@ -172,3 +170,62 @@ def test_flash_attention_engine_path(heads, dim, img, monkeypatch):
         for k in grads:
             a, b = res[0][1][k], grads[k]
             assert (a - b).norm().item() <= 3e-2 * a.norm().item() + 1e-6, k
+
+
+@pytest.mark.gpu
+def test_dropout_kernel_path():
+    """--pos_dropout / --att_dropout / --mlp_dropout on the CUDA engine: Philox dropout kernels, no eager fallback.
+    (a) keep fraction and scaling, (b) same key -> same mask (recompute consistency), (c) a checkpointed and a
+    non-checkpointed model give the same gradients (the recompute regenerates the masks), (d) training still learns."""
+    from vit_10b_fsdp_example_b200.config import ViTConfig
+    from vit_10b_fsdp_example_b200.ops import cuda_ops as co
+    from vit_10b_fsdp_example_b200.parallel import FSDPViT, ShardedAdamW
+
+    dev = torch.device("cuda")
+    x = torch.ones(1 << 20, device=dev, dtype=torch.bfloat16)
+    n0 = co.launch_count()
+    y1, y2, y3 = co.dropout(x, 0.25, 12345), co.dropout(x, 0.25, 12345), co.dropout(x, 0.25, 12346)
+    assert co.launch_count() - n0 == 3
+    keep = (y1 != 0).float().mean().item()
+    assert abs(keep - 0.75) < 5e-3, keep
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    assert abs(y1.float().max().item() - 1.0 / 0.75) < 1e-2
+    cfg = ViTConfig(image_size=112, patch_size=14, embed_dim=256, num_heads=4, num_blocks=2, mlp_ratio=4.0,
+                    num_classes=96, pos_dropout=0.1, att_dropout=0.1, mlp_dropout=0.1)
+    g = torch.Generator().manual_seed(0)
+    xi = torch.randn(8, 3, 112, 112, generator=g).to(dev)
+    yi = torch.randint(0, 96, (8,), generator=g).to(dev)
+    grads = []
+    for ckpt, keepb in ((True, 0), (False, 0), (True, 2)):
+        model = FSDPViT(cfg, device=dev, dtype=torch.bfloat16, seed=4, grad_ckpt=ckpt, ckpt_keep_blocks=keepb)
+        model.forward_backward(xi, yi)
+        grads.append(_full_grads(model))
+    for other in grads[1:]:
+        for k in grads[0]:
+            a, b = grads[0][k], other[k]
+            assert (a - b).norm().item() <= 2e-2 * a.norm().item() + 1e-6, k
+    model = FSDPViT(cfg, device=dev, dtype=torch.bfloat16, seed=4)
+    opt = ShardedAdamW(model, lr=1e-3, weight_decay=0.0)
+    losses = []
+    for _ in range(8):
+        losses.append(model.forward_backward(xi, yi).item())
+        model.clip_grad_norm_(1.0)
+        opt.step()
+    assert losses[-1] < losses[0], losses
+    model.eval()
+    a, b = model(xi), model(xi)  # inference: dropout off -> deterministic
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_mean_pool_kernels():
+    from vit_10b_fsdp_example_b200.ops import cuda_ops as co, torch_ops as to
+
+    B, N, D = 6, 196, 1024
+    xn = torch.randn(B * N, D, device="cuda").to(torch.bfloat16)
+    got, ref = co.mean_pool(xn, B, N).float(), to.mean_pool(xn.float(), B, N)
+    assert (got - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-3
+    dp = torch.randn(B, D, device="cuda").to(torch.bfloat16)
+    got, ref = co.mean_pool_bwd(dp, B, N).float(), to.mean_pool_bwd(dp.float(), B, N)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 8e-3 * ref.abs().max().item() + 1e-6

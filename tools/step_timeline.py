@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4, help="untraced timed steps (CUDA events) before the traced one")
     ap.add_argument("--model", default="vit10b")
     ap.add_argument("--device_index", type=int, default=-1)
+    ap.add_argument("--backend", default="sm100", choices=["sm100", "torchdist"])
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -57,7 +58,7 @@ def main():
     image, patch, dim, heads, _, mlp, _ = MODELS[args.model]
     vcfg = ViTConfig(image_size=image, patch_size=patch, embed_dim=dim, num_heads=heads, num_blocks=args.blocks,
                      mlp_ratio=mlp, num_classes=1000)
-    model = FSDPViT(vcfg, world=world, rank=rank, device=dev, dtype=torch.bfloat16, backend="sm100",
+    model = FSDPViT(vcfg, world=world, rank=rank, device=dev, dtype=torch.bfloat16, backend=args.backend,
                     init_device="cuda", ckpt_keep_blocks=args.keep)
     opt = ShardedAdamW(model, lr=1e-3, weight_decay=0.1)
     x = torch.zeros(args.batch, 3, image, image, device=dev)

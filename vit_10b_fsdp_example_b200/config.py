@@ -58,6 +58,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
                         help="collective backend: sm100 = symmetric-memory NVLink kernels, nccl/gloo = torch.distributed")
     parser.add_argument("--device", type=str, default="auto", choices=["auto", "cuda", "cpu"])
     parser.add_argument("--seed", type=int, default=0, help="parameter-init seed (identical on all ranks)")
+    parser.add_argument("--init_device", type=str, default="auto", choices=["auto", "cuda", "cpu"],
+                        help="where random initial parameters are drawn: auto = on the GPU for CUDA runs (fast, the "
+                             "benchmarked path), on the host with --shard_on_cpu or --device cpu")
     parser.add_argument("--max_steps", type=int, default=0, help="stop every epoch after this many steps (0 = full epoch)")
     parser.add_argument("--nproc", type=int, default=0,
                         help="processes to spawn when not launched by torchrun (0 = one per visible GPU, 1 on CPU)")

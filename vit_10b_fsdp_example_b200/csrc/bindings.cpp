@@ -167,6 +167,21 @@ void gelu_fwd(Tensor u, Tensor g) {
     c10::cuda::CUDAGuard guard(u.device());
     b200::gelu_fwd(bf16_ptr(u), bf16_mut(g), u.numel(), cur_stream());
 }
+void dropout(Tensor x, Tensor y, double p, int64_t key) {
+    c10::cuda::CUDAGuard guard(x.device());
+    TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && x.numel() == y.numel(), "dropout: contiguous, same size");
+    b200::dropout(bf16_ptr(x), bf16_mut(y), x.numel(), (float)p, (uint64_t)key, cur_stream());
+}
+void meanpool_fwd(Tensor xn, Tensor pooled, int64_t B, int64_t N) {
+    c10::cuda::CUDAGuard guard(xn.device());
+    TORCH_CHECK(xn.is_contiguous() && pooled.is_contiguous() && xn.numel() == pooled.numel() * N, "meanpool: bad shapes");
+    b200::meanpool_fwd(bf16_ptr(xn), bf16_mut(pooled), (int)B, (int)N, (int)(pooled.numel() / B), cur_stream());
+}
+void meanpool_bwd(Tensor dpooled, Tensor dxn, int64_t B, int64_t N) {
+    c10::cuda::CUDAGuard guard(dxn.device());
+    TORCH_CHECK(dxn.is_contiguous() && dpooled.is_contiguous() && dxn.numel() == dpooled.numel() * N, "meanpool: bad shapes");
+    b200::meanpool_bwd(bf16_ptr(dpooled), bf16_mut(dxn), (int)B, (int)N, (int)(dpooled.numel() / B), cur_stream());
+}
 void dgelu_mul(Tensor dg, Tensor u, Tensor du) {
     c10::cuda::CUDAGuard guard(u.device());
     b200::dgelu_mul(bf16_ptr(dg), bf16_ptr(u), bf16_mut(du), u.numel(), cur_stream());
@@ -323,6 +338,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("im2col", &im2col);
     m.def("gelu_fwd", &gelu_fwd);
     m.def("dgelu_mul", &dgelu_mul);
+    m.def("dropout", &dropout);
+    m.def("meanpool_fwd", &meanpool_fwd);
+    m.def("meanpool_bwd", &meanpool_bwd);
     m.def("colsum", &colsum);
     m.def("sumsq", &sumsq);
     m.def("adamw_split", &adamw_split);

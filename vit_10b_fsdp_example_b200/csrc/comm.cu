@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -61,6 +62,26 @@ __device__ __forceinline__ void st_stream_v4(void* ptr, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+}
+// Streaming stores whose lines are the first to leave L2: the gathered parameters / reduced gradients are consumed
+// milliseconds later, while the co-running GEMM lives off the A/B panels it keeps L2-resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_stream_v4_hint(void* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_stream_v4_hint(const void* ptr, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(ptr), "l"(pol)
+                 : "memory");
+    return r;
 }
 __device__ __forceinline__ void st_release_sys(uint32_t* ptr, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
@@ -179,8 +200,9 @@ __device__ __forceinline__ void sync_end(const SyncArgs& s, uint32_t seq) {
 // seg_table row (all-gather): [src_rank, src_off_bytes, dst_off_bytes, nbytes, chunk_prefix]
 __global__ void __launch_bounds__(kCommThreads, 8) p2p_all_gather_kernel(PeerPtrs peers, uint8_t* __restrict__ out,
                                                                          const int64_t* __restrict__ seg, int nseg,
-                                                                         int64_t total_chunks) {
+                                                                         int64_t total_chunks, int l2_hint) {
     int s = 0;
+    const uint64_t pol = l2_evict_first_policy();
     for (int64_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         while (s + 1 < nseg && seg[(s + 1) * 5 + 4] <= c) ++s;
         const int64_t* row = seg + s * 5;
@@ -192,12 +214,15 @@ __global__ void __launch_bounds__(kCommThreads, 8) p2p_all_gather_kernel(PeerPtr
 #pragma unroll
         for (int u = 0; u < kAgUnroll; ++u) {
             const int64_t i = threadIdx.x + u * kCommThreads;
-            if (i < nvec) v[u] = ld_stream_v4(src + i * 16);
+            if (i < nvec) v[u] = l2_hint ? ld_stream_v4_hint(src + i * 16, pol) : ld_stream_v4(src + i * 16);
         }
 #pragma unroll
         for (int u = 0; u < kAgUnroll; ++u) {
             const int64_t i = threadIdx.x + u * kCommThreads;
-            if (i < nvec) st_stream_v4(dst + i * 16, v[u]);
+            if (i < nvec) {
+                if (l2_hint) st_stream_v4_hint(dst + i * 16, v[u], pol);
+                else st_stream_v4(dst + i * 16, v[u]);
+            }
         }
     }
 }
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(kCommThreads, kNvls && !kAdam ? 8 : 5)
                           float* __restrict__ out, const int64_t* __restrict__ seg, int nseg, int64_t total_chunks,
                           float scale, float* __restrict__ sumsq_out, AdamFuse adam) {
     const uint32_t seq = sync_begin(sync);
+    const uint64_t pol = l2_evict_first_policy();
     float sq = 0.f;
     int s = 0;
     constexpr int kVec = kBf16In ? 8 : 4;  // elements per 16 B
@@ -299,9 +325,15 @@ __global__ void __launch_bounds__(kCommThreads, kNvls && !kAdam ? 8 : 5)
                         adam.lo[e + q] = static_cast<int16_t>(nb - (h << 16));
                     }
                 } else {
-                    float4* d4 = reinterpret_cast<float4*>(dst + i * kVec);
-                    d4[0] = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
-                    if constexpr (kVec == 8) d4[1] = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+                    uint4 o0, o1;
+                    o0.x = __float_as_uint(acc[u][0]), o0.y = __float_as_uint(acc[u][1]);
+                    o0.z = __float_as_uint(acc[u][2]), o0.w = __float_as_uint(acc[u][3]);
+                    st_stream_v4_hint(dst + i * kVec, o0, pol);
+                    if constexpr (kVec == 8) {
+                        o1.x = __float_as_uint(acc[u][4]), o1.y = __float_as_uint(acc[u][5]);
+                        o1.z = __float_as_uint(acc[u][6]), o1.w = __float_as_uint(acc[u][7]);
+                        st_stream_v4_hint(dst + i * kVec + 4, o1, pol);
+                    }
                 }
             }
         }
@@ -446,8 +478,9 @@ void p2p_all_gather(const std::vector<int64_t>& peer_ptrs, int rank, void* out, 
                     int nseg, int64_t total_chunks, int max_ctas, cudaStream_t stream) {
     (void)rank;
     if (total_chunks == 0) return;
+    static const int l2_hint = getenv("B200_COMM_L2_HINT") ? atoi(getenv("B200_COMM_L2_HINT")) : 1;
     p2p_all_gather_kernel<<<grid_for(total_chunks, max_ctas), kCommThreads, 0, stream>>>(
-        to_peers(peer_ptrs), static_cast<uint8_t*>(out), seg_table_dev, nseg, total_chunks);
+        to_peers(peer_ptrs), static_cast<uint8_t*>(out), seg_table_dev, nseg, total_chunks, l2_hint);
     check_launch("p2p_all_gather");
 }
 

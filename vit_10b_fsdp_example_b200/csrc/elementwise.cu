@@ -473,6 +473,102 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dropout on the kernel path (reference flags --pos_dropout / --att_dropout / --mlp_dropout, run_vit_training.py:
+// 345-347): y = x * keep / (1 - p) with keep drawn from Philox-4x32-10, counter = index of the 16-byte vector, key =
+// the 64-bit (seed, step, site) key of the engine's DropoutCtx.  The mask is a pure function of (key, element index),
+// so the activation-checkpoint recompute and the backward pass regenerate it instead of storing it: one Philox call
+// yields 8 x 16 random bits = the 8 bf16 values of a vector (keep <=> r16 >= p * 65536).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+    uint32_t c2 = 0x5eed5eedu, c3 = 0x0b200b20u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                      int64_t nvec, uint32_t key_lo, uint32_t key_hi, uint32_t thresh16,
+                                                      float scale) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        uint32_t r[4];
+        philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), key_lo, key_hi, r);
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t r16 = (r[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+            f[q] = r16 >= thresh16 ? f[q] * scale : 0.f;
+        }
+        reinterpret_cast<uint4*>(y)[i] = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token mean-pool of the head (reference run_vit_training.py:161: x.mean(dim=1) after the final norm) and its backward.
+// Forward: pooled[b, :] = mean_n xn[b, n, :] -- a CTA column-strip sums the N tokens of one image in fp32.
+// Backward: d xn[b, n, :] = dpooled[b, :] / N for every token; written as the broadcast rows the final-LayerNorm
+// backward consumes (one pass, no [B, N, D] fp32 intermediate as in the eager expand + div).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) meanpool_fwd_kernel(const __nv_bfloat16* __restrict__ xn,
+                                                           __nv_bfloat16* __restrict__ pooled, int N, int D) {
+    const int b = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte vector (8 columns)
+    if (v >= D / 8) return;
+    const uint4* src = reinterpret_cast<const uint4*>(xn + static_cast<int64_t>(b) * N * D) + v;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {  // 4 independent loads in flight
+        uint4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = src[static_cast<int64_t>(n + u) * (D / 8)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(t[u], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+        }
+    }
+    for (; n < N; ++n) {
+        float f[8];
+        unpack8(src[static_cast<int64_t>(n) * (D / 8)], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+    const float inv = 1.0f / static_cast<float>(N);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] *= inv;
+    reinterpret_cast<uint4*>(pooled + static_cast<int64_t>(b) * D)[v] = pack8(acc);
+}
+
+__global__ void __launch_bounds__(128) meanpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled,
+                                                           __nv_bfloat16* __restrict__ dxn, int N, int D) {
+    const int b = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= D / 8) return;
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(dpooled + static_cast<int64_t>(b) * D)[v], f);
+    const float inv = 1.0f / static_cast<float>(N);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] *= inv;
+    const uint4 o = pack8(f);
+    uint4* dst = reinterpret_cast<uint4*>(dxn + static_cast<int64_t>(b) * N * D) + v;
+    for (int n = 0; n < N; ++n) dst[static_cast<int64_t>(n) * (D / 8)] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row softmax (attention probabilities), in place on a [rows, ld] bf16 matrix with `n` valid columns.
 // One warp per row; fp32 math; exp2 with pre-multiplied log2(e).
 // ------------------------------------------------------------------------------------------------
@@ -936,6 +1032,31 @@ void dgelu_mul(const __nv_bfloat16* dg, const __nv_bfloat16* u, __nv_bfloat16* d
     if (grid == 0) return;
     dgelu_mul_kernel<<<grid, 256, 0, stream>>>(dg, u, du, n / 8);
     check_launch("dgelu_mul");
+}
+
+void dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t key, cudaStream_t stream) {
+    if (n % 8 != 0) throw std::runtime_error("dropout: element count must be a multiple of 8");
+    if (!(p >= 0.f && p < 1.f)) throw std::runtime_error("dropout: p must be in [0, 1)");
+    const int grid = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256, sm_count() * 16));
+    if (grid == 0) return;
+    const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    dropout_kernel<<<grid, 256, 0, stream>>>(x, y, n / 8, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32),
+                                            thresh, 1.0f / (1.0f - static_cast<float>(thresh) / 65536.0f));
+    check_launch("dropout");
+}
+
+void meanpool_fwd(const __nv_bfloat16* xn, __nv_bfloat16* pooled, int B, int N, int D, cudaStream_t stream) {
+    if (D % 8 != 0) throw std::runtime_error("meanpool: width must be a multiple of 8");
+    dim3 grid((D / 8 + 127) / 128, B);
+    meanpool_fwd_kernel<<<grid, 128, 0, stream>>>(xn, pooled, N, D);
+    check_launch("meanpool_fwd");
+}
+
+void meanpool_bwd(const __nv_bfloat16* dpooled, __nv_bfloat16* dxn, int B, int N, int D, cudaStream_t stream) {
+    if (D % 8 != 0) throw std::runtime_error("meanpool: width must be a multiple of 8");
+    dim3 grid((D / 8 + 127) / 128, B);
+    meanpool_bwd_kernel<<<grid, 128, 0, stream>>>(dpooled, dxn, N, D);
+    check_launch("meanpool_bwd");
 }
 
 void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream) {

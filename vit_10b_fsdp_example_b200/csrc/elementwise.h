@@ -28,6 +28,12 @@ void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S
 
 void gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* g, int64_t n, cudaStream_t stream);
 void dgelu_mul(const __nv_bfloat16* dg, const __nv_bfloat16* u, __nv_bfloat16* du, int64_t n, cudaStream_t stream);
+// y = x * keep / (1 - p), keep = Philox-4x32-10(key, vector index): a pure function of (key, position), so recompute and
+// backward regenerate the mask.  p is quantised to 1/65536.  y may alias x.
+void dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t key, cudaStream_t stream);
+// pooled[b] = mean over the N tokens of image b; backward broadcasts dpooled[b] / N to every token row.
+void meanpool_fwd(const __nv_bfloat16* xn, __nv_bfloat16* pooled, int B, int N, int D, cudaStream_t stream);
+void meanpool_bwd(const __nv_bfloat16* dpooled, __nv_bfloat16* dxn, int B, int N, int D, cudaStream_t stream);
 void colsum(const __nv_bfloat16* x, float* out, int64_t rows, int C, cudaStream_t stream);
 void sumsq(const void* x, bool is_bf16, int64_t n, float* out, cudaStream_t stream);
 

@@ -107,6 +107,9 @@ def _worker(local_rank: int, fn, cfg, world: int, port: int) -> None:
 
 def launch(fn: Callable[[Runtime, Any], None], cfg) -> None:
     """Run ``fn(runtime, cfg)`` in every process of the job."""
+    # must be in the environment before the first CUDA allocation of this process and of spawned workers: the
+    # memory-aware activation policy fills HBM to within a few GB, which needs an allocator that does not fragment
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     if "RANK" in os.environ and "WORLD_SIZE" in os.environ:  # torchrun / torch.distributed.run
         rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
         local_rank = int(os.environ.get("LOCAL_RANK", rank))

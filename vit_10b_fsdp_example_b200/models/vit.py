@@ -100,26 +100,17 @@ def init_root_params(cfg: ViTConfig, gen, device="cpu") -> Dict[str, torch.Tenso
 # Dropout (reference flags --pos_dropout / --att_dropout / --mlp_dropout, default 0 -> elided)
 # ------------------------------------------------------------------------------------------------
 class DropoutCtx:
-    """Counter-based dropout masks: mask(site) is a pure function of (seed, step, site), so the
-    activation-checkpoint recompute regenerates exactly the mask the first forward used."""
+    """Counter-based dropout: the mask of a site is a pure function of (seed, step, site, position) -- a 64-bit key
+    handed to ``ops.dropout`` (Philox kernel on the GPU, seeded generator on the CPU) -- so nothing is stored: the
+    activation-checkpoint recompute and the backward pass regenerate exactly the mask the first forward used."""
 
     def __init__(self, seed: int = 0):
         self.seed = seed
         self.step = 0
         self.training = True
 
-    def mask(self, shape, p: float, site: int, device):
-        if p <= 0.0 or not self.training:
-            return None
-        gen = torch.Generator(device=device)
-        gen.manual_seed((self.seed * 1000003 + self.step) * 1000003 + site)
-        return torch.rand(shape, generator=gen, device=device) >= p
-
-
-def _apply_mask(t, mask, p):
-    if mask is None:
-        return t
-    return (t.float() * mask * (1.0 / (1.0 - p))).to(t.dtype)
+    def key(self, site: int) -> int:
+        return (((self.seed * 1000003 + self.step) * 1000003 + site) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
 
 
 # ------------------------------------------------------------------------------------------------
@@ -146,21 +137,21 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
     ag = getattr(p, "ag", None) or {}  # weights whose all-gather is fused into the GEMM that consumes them
     h1, m1, r1 = ops.ln_fwd(x, p["norm1.weight"], p["norm1.bias"], BLOCK_LN_EPS)
     qkv = ops.linear_fwd(h1, p["attn.qkv.weight"], p["attn.qkv.bias"], ag=ag.get("attn.qkv.weight"))
-    masks = {}
+    masks = {}  # site name -> dropout key (the masks themselves are regenerated, never stored)
     lse = None
     if use_drop and pa > 0:
-        masks["att"] = drop.mask((B, H, N, N), pa, site + 0, x.device)
-        a, P = ops.attention_fwd(qkv, B, N, H, hd, drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
-    elif do_save and getattr(ops, "FLASH_ATTENTION", False) and ops.flash_supported(N, hd):
+        masks["att"] = drop.key(site + 0)
+        a, P = ops.attention_fwd(qkv, B, N, H, hd, drop=(pa, masks["att"]))
+    elif do_save and ops.use_flash(N, hd):
         a, lse = ops.attention_fwd_lse(qkv, B, N, H, hd)  # backward rebuilds P from the row log-sum-exp
         P = None
     else:
         a, P = ops.attention_fwd(qkv, B, N, H, hd, need_p="P" in extras)
     if use_drop and pm > 0:
         # timm feeds `drop` to both proj_drop and the two MLP dropouts
-        masks["proj"] = drop.mask(x.shape, pm, site + 1, x.device)
+        masks["proj"] = drop.key(site + 1)
         t = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"])
-        x1 = (x.float() + _apply_mask(t, masks["proj"], pm).float()).to(x.dtype)
+        x1 = x + ops.dropout(t, pm, masks["proj"])
     else:
         x1 = ops.linear_fwd(a, p["attn.proj.weight"], p["attn.proj.bias"], residual=x)
     h2, m2, r2 = ops.ln_fwd(x1, p["norm2.weight"], p["norm2.bias"], BLOCK_LN_EPS)
@@ -170,11 +161,11 @@ def block_forward(ops, cfg: ViTConfig, p, x, B: int, save, drop: Optional[Dropou
     else:
         g, u = ops.linear_fwd(h2, p["mlp.fc1.weight"], p["mlp.fc1.bias"], act="gelu", ag=ag.get("mlp.fc1.weight")), None
     if use_drop and pm > 0:
-        masks["fc1"] = drop.mask(g.shape, pm, site + 2, x.device)
-        masks["fc2"] = drop.mask(x.shape, pm, site + 3, x.device)
-        g = _apply_mask(g, masks["fc1"], pm)
+        masks["fc1"] = drop.key(site + 2)
+        masks["fc2"] = drop.key(site + 3)
+        g = ops.dropout(g, pm, masks["fc1"])
         t = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"])
-        y = (x1.float() + _apply_mask(t, masks["fc2"], pm).float()).to(x.dtype)
+        y = x1 + ops.dropout(t, pm, masks["fc2"])
     else:
         y = ops.linear_fwd(g, p["mlp.fc2.weight"], p["mlp.fc2.bias"], residual=x1)
     if not do_save:
@@ -201,7 +192,7 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     masks = s["masks"]
     # ---- MLP ----
     if "fc2" in masks:
-        dt = _apply_mask(dy, masks["fc2"], pm)
+        dt = ops.dropout(dy, pm, masks["fc2"])
         G["mlp.fc2.bias"].copy_(ops.colsum(dt))
     else:
         dt = dy
@@ -210,12 +201,12 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     if g is None:  # not kept: re-materialise from the pre-activation
         g = ops.gelu_fwd(s["u"])
         if "fc1" in masks:
-            g = _apply_mask(g, masks["fc1"], pm)
+            g = ops.dropout(g, pm, masks["fc1"])
     ops.linear_wgrad(dt, g, out=G["mlp.fc2.weight"])
     del g
     if "fc1" in masks:
-        dg = _apply_mask(ops.linear_dgrad(dt, p["mlp.fc2.weight"]), masks["fc1"], pm)
-        du = (dg.float() * ops_dgelu(ops, s["u"])).to(dy.dtype)
+        dg = ops.dropout(ops.linear_dgrad(dt, p["mlp.fc2.weight"]), pm, masks["fc1"])
+        du = ops.dgelu_mul(dg, s["u"])
         db1 = ops.colsum(du)
     else:
         du, db1 = ops.linear_dgrad(dt, p["mlp.fc2.weight"], dgelu_preact=s["u"], want_colsum=True)
@@ -233,7 +224,7 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     G["norm2.bias"].copy_(dn2b)
     # ---- attention ----
     if "proj" in masks:
-        dt = _apply_mask(dx1, masks["proj"], pm)
+        dt = ops.dropout(dx1, pm, masks["proj"])
         G["attn.proj.bias"].copy_(ops.colsum(dt))
     else:
         dt = dx1
@@ -247,7 +238,7 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
             s["P"] = ops.attention_probs(s["qkv"], B, N, H, hd)
         if "att" in masks:
             dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True,
-                                            drop_mask=masks["att"], drop_scale=1.0 / (1.0 - pa))
+                                            drop=(pa, masks["att"]))
         else:
             dqkv, dbqkv = ops.attention_bwd(da, s["qkv"], s["P"], B, N, H, hd, want_colsum=True)
     del da
@@ -266,12 +257,6 @@ def block_backward(ops, cfg: ViTConfig, p, G, s, dy, dy_colsum, B: int):
     return dx, dx_sum
 
 
-def ops_dgelu(ops, u):
-    from ..ops import torch_ops
-
-    return torch_ops.dgelu(u)
-
-
 # ------------------------------------------------------------------------------------------------
 # Stem (patch embed + pos embed) and head (final norm, mean pool, classifier, loss)
 # ------------------------------------------------------------------------------------------------
@@ -280,16 +265,16 @@ def stem_forward(ops, cfg: ViTConfig, p, images, dtype, drop: Optional[DropoutCt
     cols = ops.patch_im2col(images, cfg.patch_size, cfg.patch_kpad, dtype)
     x0 = ops.linear_fwd(cols, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], residual=p["pos_embed"],
                         res_row_mod=cfg.num_patches)
-    mask = None
-    if drop is not None and cfg.pos_dropout > 0:
-        mask = drop.mask(x0.shape, cfg.pos_dropout, 7_000_001, x0.device)
-        x0 = _apply_mask(x0, mask, cfg.pos_dropout)
+    mask = None  # dropout key of the position-embedding dropout (reference :129,157)
+    if drop is not None and drop.training and cfg.pos_dropout > 0:
+        mask = drop.key(7_000_001)
+        x0 = ops.dropout(x0, cfg.pos_dropout, mask)
     return x0, dict(cols=cols, mask=mask, B=B)
 
 
 def stem_backward(ops, cfg: ViTConfig, p, G, s, dx0, dx0_colsum):
     if s["mask"] is not None:
-        dx0 = _apply_mask(dx0, s["mask"], cfg.pos_dropout)
+        dx0 = ops.dropout(dx0, cfg.pos_dropout, s["mask"])
         dx0_colsum = ops.colsum(dx0)
     ops.linear_wgrad(dx0, s["cols"], out=G["patch_embed.proj.weight"])
     G["patch_embed.proj.bias"].copy_(dx0_colsum)
@@ -300,7 +285,7 @@ def head_forward(ops, cfg: ViTConfig, p, x, B: int):
     """logits = head(mean_tokens(norm(x)))   (run_vit_training.py:161)"""
     N, D = cfg.num_patches, cfg.embed_dim
     xn, m, r = ops.ln_fwd(x, p["norm.weight"], p["norm.bias"], FINAL_LN_EPS)
-    pooled = xn.view(B, N, D).mean(dim=1, dtype=torch.float32).to(x.dtype)
+    pooled = ops.mean_pool(xn, B, N)
     logits = ops.linear_fwd(pooled, p["head.weight"], p["head.bias"])
     return logits, dict(x=x, m=m, r=r, pooled=pooled)
 
@@ -310,7 +295,7 @@ def head_backward(ops, cfg: ViTConfig, p, G, s, dlogits, B: int):
     ops.linear_wgrad(dlogits, s["pooled"], out=G["head.weight"])
     G["head.bias"].copy_(dlogits.sum(dim=0, dtype=torch.float32))
     dpooled = ops.linear_dgrad(dlogits, p["head.weight"])
-    dxn = (dpooled.float() / N).to(dpooled.dtype)[:, None, :].expand(B, N, D).reshape(B * N, D)
+    dxn = ops.mean_pool_bwd(dpooled, B, N)
     dx, dnw, dnb, dx_sum = ops.ln_bwd(dxn, s["x"], p["norm.weight"], s["m"], s["r"], want_dxsum=True)
     G["norm.weight"].copy_(dnw)
     G["norm.bias"].copy_(dnb)

@@ -194,6 +194,12 @@ def gelu_fwd(u):
     return g
 
 
+def dgelu_mul(dg, u):
+    du = torch.empty_like(dg)
+    _C.dgelu_mul(dg.contiguous(), u, du)
+    return du
+
+
 def colsum(x):
     out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
     _C.colsum(x, out)
@@ -207,19 +213,54 @@ FUSED_ATTENTION = _os.environ.get("B200_FUSED_ATTN", "1") != "0"
 FUSED_ATTENTION_HD160 = _os.environ.get("B200_FUSED_ATTN_HD160", "0") == "1"
 
 
-# Persistent, software-pipelined forward (csrc/attention_persist_sm100.cu): written for the hd = 160 case where the
-# one-shot kernel cannot hide its loads; not run on hardware yet -> opt in with B200_ATTN_PERSIST=1.
-ATTN_PERSIST = _os.environ.get("B200_ATTN_PERSIST", "0") == "1"
+# Persistent, software-pipelined kernels (csrc/attention_persist_sm100.cu, attention_bwd_persist_sm100.cu): one CTA per
+# SM loops over work items.  They win where only one CTA fits an SM (hd = 160: forward 632 vs 763 us one-shot, backward
+# 1622 vs 1814 us) and lose where two fit (hd = 64: 254 vs 159 us), hence the per-shape default below.
+_PERSIST_ENV = _os.environ.get("B200_ATTN_PERSIST", "")
+ATTN_PERSIST = _PERSIST_ENV == "1"
 
 
-def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0, need_p: bool = True):
+def _persist(hd: int) -> bool:
+    return ATTN_PERSIST or (_PERSIST_ENV != "0" and hd > 128)
+
+
+def dropout(x, p: float, key: int):
+    """Philox-keyed dropout kernel (csrc/elementwise.cu): the mask is a function of (key, position), never stored."""
+    xc = x.contiguous()
+    assert xc.numel() % 8 == 0, "dropout kernel works on whole 16-byte vectors"
+    y = torch.empty_like(xc)
+    _C.dropout(xc, y, float(p), int(key) & 0x7FFFFFFFFFFFFFFF)
+    return y
+
+
+def mean_pool(xn, B: int, N: int):
+    pooled = torch.empty(B, xn.shape[1], dtype=xn.dtype, device=xn.device)
+    _C.meanpool_fwd(xn, pooled, B, N)
+    return pooled
+
+
+def mean_pool_bwd(dpooled, B: int, N: int):
+    dxn = torch.empty(B * N, dpooled.shape[1], dtype=dpooled.dtype, device=dpooled.device)
+    _C.meanpool_bwd(dpooled.contiguous(), dxn, B, N)
+    return dxn
+
+
+def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop=None, need_p: bool = True):
     """Returns (out [B*N, D], P).  P = softmax probabilities [B*H, N, ldp] for the backward, or None when
-    need_p=False and the fused kernel ran (scores never reach HBM then)."""
-    if drop_mask is not None:  # attention dropout > 0: rare path, run the reference math
-        return torch_ops.attention_fwd(qkv, B, N, H, hd, drop_mask, drop_scale)
+    need_p=False and the fused kernel ran (scores never reach HBM then).
+    drop = (p, key): attention dropout.  The probabilities are materialised (un-fused path), the dropped copy that
+    feeds P V comes from the Philox dropout kernel; the returned P is the un-dropped one (backward regenerates the mask)."""
     D = H * hd
     ldp = _pad8(N)
-    if ATTN_PERSIST and not need_p and _C.attention_fwd_persist_supported(N, hd):
+    if drop is not None:
+        p = attention_probs(qkv, B, N, H, hd)
+        pd = dropout(p, drop[0], drop[1])
+        out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
+        ld3 = qkv.stride(0)
+        gemm_raw(pd, ldp, 0, qkv[:, 2 * D:], ld3, 1, out, D, N, hd, N,
+                 batch=(H, B, N * ldp, H * N * ldp, hd, N * ld3, hd, N * D))
+        return out, p
+    if _persist(hd) and FUSED_ATTENTION and not need_p and _C.attention_fwd_persist_supported(N, hd):
         out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
         _C.attention_fwd_persist(qkv, out, None, B, N, H, hd)
         return out, None
@@ -252,17 +293,18 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_sca
     return out, p
 
 
-# Fused (flash-style) forward + backward pair: forward keeps the log-sum-exp, csrc/attention_bwd_sm100.cu rebuilds P.
-# Kernel numerics are validated on B200 (tests/test_gpu_attention.py::test_fused_attention_backward) and the pair is
-# 1.75x faster than GEMMs + softmax kernels at ViT-L shapes (404 vs 706 us incl. P re-materialisation) but not yet at
-# hd = 160 (1833 vs 1783 us: one CTA per SM, nothing overlaps its load / epilogue phases).  The model-level switch
-# stays opt-in (B200_FUSED_ATTN_BWD=1) until the engine path has been run on hardware too.
-FLASH_ATTENTION = _os.environ.get("B200_FUSED_ATTN_BWD", "0") == "1"
-
-
-# N > 256 (336 px: 576 tokens) goes through the two-pass long-sequence forward; that kernel and the N > 256 use of the
-# backward kernels have not run on hardware yet (B200_FUSED_ATTN_LONG=1 to try them).
-FLASH_LONG = _os.environ.get("B200_FUSED_ATTN_LONG", "0") == "1"
+# Fused (flash-style) forward + backward pair: the forward keeps only the row log-sum-exp, the backward kernels
+# (csrc/attention_bwd_sm100.cu) rebuild P tile by tile; scores never reach HBM.  Measured on B200 (CUDA events,
+# profiles/r2_attention.md), forward + backward incl. the P re-materialisation the un-fused path needs:
+#   ViT-L  (B128 N196 H16 hd64) : fused 159 + 387 us   vs un-fused 279 + 500 + 204 us   -> fused by default
+#   336 px (B56 N576 H32 hd160) : fused 1584 + 3032 us vs un-fused 1424 + 2459 + 1088 us, and P alone would be
+#                                 1.2 GB per block                                       -> fused by default
+#   ViT-10B (B128 N256 H32 hd160): fused (persistent) 632 + 1622 us vs un-fused 664 + 1356 (+426 if P is not kept)
+#                                 -> un-fused while HBM can hold P, see use_flash()
+# B200_FUSED_ATTN_BWD=0 / 1 forces the choice.
+_FLASH_ENV = _os.environ.get("B200_FUSED_ATTN_BWD", "")
+FLASH_ATTENTION = _FLASH_ENV != "0"
+FLASH_LONG = _os.environ.get("B200_FUSED_ATTN_LONG", "1") != "0"
 
 
 def flash_supported(N: int, hd: int) -> bool:
@@ -271,10 +313,19 @@ def flash_supported(N: int, hd: int) -> bool:
     return bool(FLASH_LONG and _C.attention_fwd_long_supported(N, hd) and _C.attention_bwd_supported(N, hd))
 
 
+def use_flash(N: int, hd: int) -> bool:
+    """Model-level policy: run the attention core through the fused forward (log-sum-exp) + fused backward pair?"""
+    if not FLASH_ATTENTION or not flash_supported(N, hd):
+        return False
+    if _FLASH_ENV == "1":
+        return True
+    return hd <= 128 or N > 256
+
+
 def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
     out = torch.empty(B * N, H * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    if ATTN_PERSIST and _C.attention_fwd_persist_supported(N, hd):
+    if _persist(hd) and _C.attention_fwd_persist_supported(N, hd):
         _C.attention_fwd_persist(qkv, out, lse, B, N, H, hd)
     elif N <= 256:
         _C.attention_fwd(qkv, out, lse, None, B, N, H, hd)
@@ -286,7 +337,7 @@ def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
 def attention_bwd_lse(dout, qkv, out, lse, B: int, N: int, H: int, hd: int, want_colsum: bool = False):
     dqkv = torch.empty(B * N, 3 * H * hd, dtype=qkv.dtype, device=qkv.device)
     delta = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd, ATTN_PERSIST)
+    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd, _persist(hd))
     return (dqkv, colsum(dqkv)) if want_colsum else dqkv
 
 
@@ -304,10 +355,8 @@ def attention_probs(qkv, B: int, N: int, H: int, hd: int):
     return p
 
 
-def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,
-                  drop_scale: float = 1.0):
-    if drop_mask is not None:
-        return torch_ops.attention_bwd(dout, qkv, p, B, N, H, hd, want_colsum, drop_mask, drop_scale)
+def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop=None):
+    """drop = (p, key) of the forward: the dropped probabilities (for dV) and the mask on dP are regenerated."""
     D = H * hd
     ldp = p.shape[2]
     ld3 = qkv.stride(0)
@@ -320,14 +369,18 @@ def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bo
     bq = (hd, N * ld3)               # ... of q/k/v inside qkv
     bo = (hd, N * ldo)
     bd = (hd, N * 3 * D)             # ... of dq/dk/dv inside dqkv
-    # dV = P^T dO
-    gemm_raw(p, ldp, 1, dout, ldo, 1, dv, 3 * D, N, hd, N, batch=(H, B, *bp, *bo, *bd),
+    # dV = P^T dO   (with attention dropout: the dropped P that fed the forward P V)
+    pv = p if drop is None else dropout(p, drop[0], drop[1])
+    gemm_raw(pv, ldp, 1, dout, ldo, 1, dv, 3 * D, N, hd, N, batch=(H, B, *bp, *bo, *bd),
              colsum=cs[2 * D:] if want_colsum else None, colsum_bi_stride=hd)
+    del pv
     # dP = dO V^T
     dp = torch.empty_like(p)
     if ldp != N:
         dp[:, :, N:].zero_()
     gemm_raw(dout, ldo, 0, v, ld3, 0, dp, ldp, N, N, hd, batch=(H, B, *bo, *bq, *bp))
+    if drop is not None:
+        _C.dropout(dp, dp, float(drop[0]), int(drop[1]) & 0x7FFFFFFFFFFFFFFF)  # same key and shape -> same mask
     # dS = scale * P * (dP - rowsum(dP * P))   (in place)
     _C.softmax_bwd(dp, p, B * H * N, N, ldp, hd ** -0.5)
     # dQ = dS K ; dK = dS^T Q

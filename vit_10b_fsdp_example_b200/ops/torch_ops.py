@@ -61,6 +61,11 @@ def gelu_fwd(u):
     return F.gelu(_f32(u)).to(u.dtype)
 
 
+def dgelu_mul(dg, u):
+    """du = dg * gelu'(u)  (exact erf GELU)."""
+    return (_f32(dg) * dgelu(u)).to(dg.dtype)
+
+
 def dgelu(u):
     uf = _f32(u)
     cdf = 0.5 * (1.0 + torch.erf(uf * (1.0 / math.sqrt(2.0))))
@@ -116,14 +121,34 @@ def colsum(x):
 # Attention core (timm Attention: softmax(q k^T * hd^-0.5) v, no mask) -- run_vit_training.py:134
 # qkv is the packed [T, 3*D] projection; head h of q lives at columns [h*hd, (h+1)*hd).
 # ------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop_mask=None, drop_scale: float = 1.0, need_p: bool = True):
+def dropout(x, p: float, key: int):
+    """y = x * keep / (1 - p); keep is a pure function of (key, position), so the checkpoint recompute and the
+    backward pass regenerate it instead of storing it (reference: nn.Dropout inside timm Block / after pos_embed,
+    run_vit_training.py:129,138-139)."""
+    gen = torch.Generator(device=x.device)
+    gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
+    keep = torch.rand(x.shape, generator=gen, device=x.device) >= p
+    return (x.float() * keep * (1.0 / (1.0 - p))).to(x.dtype)
+
+
+def mean_pool(xn, B: int, N: int):
+    """[B*N, D] -> [B, D]: mean over the tokens of an image (run_vit_training.py:161)."""
+    return xn.view(B, N, -1).mean(dim=1, dtype=torch.float32).to(xn.dtype)
+
+
+def mean_pool_bwd(dpooled, B: int, N: int):
+    """d(mean over tokens): every token row of image b receives dpooled[b] / N."""
+    D = dpooled.shape[1]
+    return (dpooled.float() / N).to(dpooled.dtype)[:, None, :].expand(B, N, D).reshape(B * N, D)
+
+
+def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop=None, need_p: bool = True):
+    """drop = (p, key): attention dropout on the probabilities (timm Attention.attn_drop)."""
     D = H * hd
     q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)  # [B, H, N, hd]
     s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
     p = torch.softmax(s, dim=-1).to(qkv.dtype)
-    pd = p
-    if drop_mask is not None:
-        pd = (p * drop_mask * drop_scale).to(qkv.dtype)
+    pd = p if drop is None else dropout(p, drop[0], drop[1])
     o = (_f32(pd) @ v).permute(0, 2, 1, 3).reshape(B * N, D).to(qkv.dtype)
     return o, p
 
@@ -135,6 +160,10 @@ FLASH_ATTENTION = False
 
 def flash_supported(N: int, hd: int) -> bool:
     return True
+
+
+def use_flash(N: int, hd: int) -> bool:
+    return FLASH_ATTENTION
 
 
 def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
@@ -168,17 +197,17 @@ def attention_probs(qkv, B: int, N: int, H: int, hd: int):
     return torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1).to(qkv.dtype)
 
 
-def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop_mask=None,
-                  drop_scale: float = 1.0):
+def attention_bwd(dout, qkv, p, B: int, N: int, H: int, hd: int, want_colsum: bool = False, drop=None):
     D = H * hd
     q, k, v = _f32(qkv).view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
     do = _f32(dout).view(B, N, H, hd).permute(0, 2, 1, 3)  # [B, H, N, hd]
     pf = _f32(p)
-    pdrop = pf if drop_mask is None else (pf * drop_mask * drop_scale).to(qkv.dtype).float()
+    pdrop = pf if drop is None else dropout(p, drop[0], drop[1]).float()
     dv = pdrop.transpose(-1, -2) @ do
-    dp = (do @ v.transpose(-1, -2)).to(qkv.dtype).float()
-    if drop_mask is not None:
-        dp = dp * drop_mask * drop_scale
+    dp = (do @ v.transpose(-1, -2)).to(qkv.dtype)
+    if drop is not None:
+        dp = dropout(dp, drop[0], drop[1])  # same key, same shape -> same mask
+    dp = dp.float()
     ds = (hd ** -0.5) * pf * (dp - (dp * pf).sum(dim=-1, keepdim=True))
     ds = ds.to(qkv.dtype).float()
     dq = ds @ k

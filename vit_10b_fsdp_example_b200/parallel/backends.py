@@ -293,7 +293,7 @@ class Sm100Backend(TorchDistBackend):
         return t
 
     def all_reduce_scalars_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
-        if self.world > 1:
+        if self.world > 1 and not self._local_only:
             assert t.dtype == torch.float32 and t.numel() <= 16
             # flag / scratch slot 4 or 5, alternating with the device-side sequence number (counter 3)
             self._C.allreduce_scalars(self._flag_ptrs, self._scratch_ptrs, self.rank, self.world, 4, 0, t,
