@@ -72,3 +72,22 @@ def full_grads_of(model):
         for n, v in u.layout.param_views(u.full_grad.float()).items():
             out[prefix + n] = v.clone()
     return out
+
+
+def assert_close_elementwise(got, ref, rtol=2e-2, atol_rel=2e-2, what=""):
+    """Per-element bound |got - ref| <= atol + rtol * |ref| with atol = atol_rel * mean|ref|.
+
+    A max-normalised check (max|err| / max|ref|) is blind to errors in small-magnitude outputs; this one holds every
+    element to a relative tolerance plus an absolute floor tied to the *typical* magnitude of the tensor (bf16 has
+    2^-8 relative precision; sums of many bf16 products carry an absolute error proportional to the typical term)."""
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    atol = atol_rel * ref.abs().mean().item() + 1e-12
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = err > bound
+    if bad.any():
+        i = (err - bound).argmax().item()
+        raise AssertionError(f"{what}: {int(bad.sum())} of {bad.numel()} elements out of tolerance; worst: got "
+                             f"{got.flatten()[i].item():.6g} ref {ref.flatten()[i].item():.6g} "
+                             f"(atol {atol:.3g}, rtol {rtol})")

@@ -1,15 +1,20 @@
 """Attention core (batched tcgen05 GEMMs + fused softmax) vs the fp32 reference."""
+import os
+import sys
+
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
 
 def _close(got, ref, rel=3e-2):
-    got, ref = got.float(), ref.float()
-    err = (got - ref).abs().max().item()
-    denom = ref.abs().max().item() + 1e-6
-    assert err / denom < rel, f"max abs err {err} vs ref max {denom}"
+    """Per-element relative + absolute bound (tests/helpers.py), not a max-normalised one."""
+    from helpers import assert_close_elementwise
+
+    assert_close_elementwise(got, ref, rtol=rel, atol_rel=rel)
 
 
 @pytest.mark.parametrize("B,N,H,hd", [(2, 256, 4, 160), (3, 196, 3, 64), (1, 576, 2, 160)])
@@ -44,7 +49,10 @@ def test_fused_attention_forward(B, N, H, hd):
     _close(p.view(B, H, N, -1)[..., :N], pr)
     out2, p2 = co.attention_fwd(qkv, B, N, H, hd, need_p=False)
     assert p2 is None
-    assert torch.equal(out2, out)
+    if hd <= 128:
+        assert torch.equal(out2, out)
+    else:  # hd = 160: the P-less forward runs on the persistent kernel (different accumulation order)
+        _close(out2, out, rel=1e-2)
     lse = torch.empty(B * H, N, device="cuda")
     out3 = torch.empty_like(out)
     co._C.attention_fwd(qkv, out3, lse, None, B, N, H, hd)

@@ -1,6 +1,11 @@
 """Memory-bound sm_100a kernels vs the fp32 PyTorch reference ops."""
+import os
+import sys
+
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -16,10 +21,10 @@ def _rand(*shape, scale=1.0):
 
 
 def _close(got, ref, rel=2e-2):
-    got, ref = got.float(), ref.float()
-    err = (got - ref).abs().max().item()
-    denom = ref.abs().max().item() + 1e-6
-    assert err / denom < rel, f"max abs err {err} vs ref max {denom}"
+    """Per-element relative + absolute bound (tests/helpers.py), not a max-normalised one."""
+    from helpers import assert_close_elementwise
+
+    assert_close_elementwise(got, ref, rtol=rel, atol_rel=rel)
 
 
 @pytest.mark.parametrize("rows,D", [(300, 192), (257, 1024), (512, 5120)])
@@ -38,6 +43,28 @@ def test_layernorm(rows, D):
     _close(dw, dwr)
     _close(db, dbr)
     _close(dxs, dxsr, rel=3e-2)
+
+
+@pytest.mark.parametrize("rows,D,res,dxsum", [(1000, 5120, False, True), (777, 5120, True, False), (600, 4096, True, True),
+                                              (300, 2560, False, False), (4096, 5120, True, True)])
+def test_layernorm_bwd_stream(rows, D, res, dxsum):
+    """Wide-row backward (csrc/layernorm_stream.cu: cp.async.bulk row ring, register column sums): every combination
+    of residual-gradient input / dx column sums, row counts that do and do not divide by the SM count."""
+    co, to = _mods()
+    x, w, b = _rand(rows, D) * 1.5 + 3.0, _rand(D), _rand(D)   # |mean| >> std on purpose
+    _, mean, rstd = co.ln_fwd(x, w, b, 1e-5)
+    dy = _rand(rows, D)
+    dres = _rand(rows, D) if res else None
+    dx, dw, db, dxs = co.ln_bwd(dy, x, w, mean, rstd, dres=dres, want_dxsum=dxsum)
+    dxr, dwr, dbr, dxsr = to.ln_bwd(dy.float(), x.float(), w.float(), mean, rstd,
+                                    dres=dres.float() if res else None, want_dxsum=dxsum)
+    _close(dx, dxr)
+    _close(dw, dwr)
+    _close(db, dbr)
+    if dxsum:
+        _close(dxs, dxsr, rel=3e-2)
+    else:
+        assert dxs is None
 
 
 @pytest.mark.parametrize("n,ld", [(256, 256), (196, 200), (576, 576), (64, 64)])

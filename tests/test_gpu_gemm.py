@@ -1,6 +1,11 @@
 """tcgen05 GEMM vs an fp32 PyTorch reference (all operand majors, tile widths, fused epilogues)."""
+import os
+import sys
+
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -16,10 +21,10 @@ def _rand(*shape, scale=1.0):
 
 
 def _close(got, ref, rel=2e-2):
-    got, ref = got.float(), ref.float()
-    err = (got - ref).abs().max().item()
-    denom = ref.abs().max().item() + 1e-6
-    assert err / denom < rel, f"max abs err {err} vs ref max {denom}"
+    """Per-element relative + absolute bound (tests/helpers.py), not a max-normalised one."""
+    from helpers import assert_close_elementwise
+
+    assert_close_elementwise(got, ref, rtol=rel, atol_rel=rel)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 768, 320), (1000, 520, 200), (128, 1000, 5120),
@@ -91,3 +96,33 @@ def test_persistent_many_tiles_and_repeat():
     for _ in range(3):
         y = ops.linear_fwd(x, w)
         _close(y, ref)
+
+
+@pytest.mark.parametrize("which", ["qkv_fwd", "fc2_fwd", "fc2_dgrad_dgelu", "fc1_wgrad"])
+def test_real_vit10b_shapes(which):
+    """The GEMMs of one ViT-10B block at the benchmarked size (32768 tokens, D 5120, FFN 20480) against an fp32
+    reference computed on a strided sample of output rows / columns (the full fp32 product would take minutes)."""
+    ops = _ops()
+    T, D, F = 32768, 5120, 20480
+    rows = torch.arange(0, T, 257, device="cuda")
+    if which == "qkv_fwd":
+        x, w, b = _rand(T, D), _rand(3 * D, D, scale=0.02), _rand(3 * D)
+        y = ops.linear_fwd(x, w, b)
+        _close(y[rows], x[rows].float() @ w.float().t() + b.float())
+    elif which == "fc2_fwd":  # K = 20480, residual epilogue
+        g, w, b, r = _rand(T, F, scale=0.5), _rand(D, F, scale=0.01), _rand(D), _rand(T, D)
+        y = ops.linear_fwd(g, w, b, residual=r)
+        _close(y[rows], g[rows].float() @ w.float().t() + b.float() + r[rows].float())
+    elif which == "fc2_dgrad_dgelu":  # MN-major B, dGELU epilogue + column sums
+        from vit_10b_fsdp_example_b200.ops import torch_ops as to
+
+        dy, w, u = _rand(T, D), _rand(D, F, scale=0.02), _rand(T, F)
+        du, cs = ops.linear_dgrad(dy, w, dgelu_preact=u, want_colsum=True)
+        ref = (dy[rows].float() @ w.float()) * to.dgelu(u[rows].float())
+        _close(du[rows], ref)
+        _close(cs, du.float().sum(dim=0), rel=2e-2)
+    else:  # wgrad: both operands MN-major, reduction over all 32768 tokens
+        du, h = _rand(T, F, scale=0.5), _rand(T, D)
+        dw = ops.linear_wgrad(du, h)
+        cols = torch.arange(0, F, 113, device="cuda")
+        _close(dw[cols], du[:, cols].float().t() @ h.float())

@@ -21,7 +21,7 @@ BUILD_DIR = os.path.join(CSRC, "build")
 SO_PATH = os.path.join(PKG_DIR, "_C.so")
 
 CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "comm.cu", "attention_sm100.cu", "attention_bwd_sm100.cu",
-              "attention_persist_sm100.cu", "attention_bwd_persist_sm100.cu"]
+              "attention_persist_sm100.cu", "attention_bwd_persist_sm100.cu", "layernorm_stream.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 
 NVCC_FLAGS = [

@@ -41,7 +41,16 @@ struct PersistParams {
     float scale_log2, scale;
     __nv_bfloat16* out;
     float* lse;      // optional
+    long long* trace;  // optional in-kernel timeline of CTA 0: clock64 stamps, 16 slots per work item (see kTr*)
+    int trace_items;
 };
+
+// trace slots (per item): who / what
+enum { kTrQkIssued = 0, kTrQkFull = 1, kTrSIssue = 2, kTrAccEmpty = 3, kTrPv0 = 4, kTrSFull = 8, kTrPass1 = 9,
+       kTrPass2 = 10, kTrAccFull = 11, kTrEpiDone = 12 };
+__device__ __forceinline__ void stamp(const PersistParams& p, int item, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && item < p.trace_items) p.trace[item * 16 + slot] = clock64();
+}
 
 template <int HD>
 struct PersistCfg {
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
                 if (i + 1 < n_items) {  // Q / K of the next item as soon as this item's S MMAs have drained them
                     mbar_wait(qk_empty, i & 1);
                     load_qk(i + 1);
+                    stamp(p, i + 1, kTrQkIssued);
                 }
                 for (int j = first; j < nkt; ++j) load_v(i, j);
             }
@@ -166,7 +176,9 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
             for (int i = 0; i < n_items; ++i) {
                 mbar_wait(qk_full, i & 1);
+                stamp(p, i, kTrQkFull);
                 if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
+                stamp(p, i, kTrSIssue);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
@@ -178,10 +190,12 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
                 umma_commit<1>(s_full);
                 umma_commit<1>(qk_empty);
                 if (i > 0) mbar_wait(acc_empty, (i - 1) & 1);
+                stamp(p, i, kTrAccEmpty);
                 for (int j = 0; j < nkt; ++j) {
                     const int t = i * nkt + j, st = t & 1;
                     mbar_wait(&v_full[st], (t >> 1) & 1);
                     mbar_wait(&e_full[st], (t >> 1) & 1);
+                    if (j < 4) stamp(p, i, kTrPv0 + j);
                     tc_fence_after();
                     const uint8_t* se = sE + st * C::kEBytes;
                     const uint8_t* sv = sV + st * C::kVBytes;
@@ -208,6 +222,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             const int q = qb * 128 + static_cast<int>(r);
             const bool row_ok = q < p.N;
             mbar_wait(s_full, i & 1);
+            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrSFull);
             tc_fence_after();
             float mx = -INFINITY;
             for (int c = 0; c < nkt * 2; ++c) {
@@ -220,6 +235,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             }
             const float m_scaled = mx * p.scale_log2;
             float sum = 0.f;
+            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrPass1);
             for (int j = 0; j < nkt; ++j) {
                 const int t = i * nkt + j, eb = t & 1;
                 if (t >= 2) mbar_wait(&e_empty[eb], ((t >> 1) - 1) & 1);
@@ -252,11 +268,13 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty);  // S of the next item may overwrite the score columns
+            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrPass2);
             const float inv = 1.0f / sum;
             const int64_t bh = static_cast<int64_t>(b) * p.H + h;
             if (p.lse != nullptr && row_ok) p.lse[bh * p.N + q] = mx * p.scale + __logf(sum);
 
             mbar_wait(acc_full, i & 1);
+            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrAccFull);
             tc_fence_after();
             __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.N + q) * p.D + h * HD;
 #pragma unroll 1
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);  // the PV MMAs of the next item may overwrite O
+            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrEpiDone);
         }
     }
     __syncthreads();
@@ -318,6 +337,11 @@ bool attention_fwd_persist_supported(int N, int hd) {
     return N > 128 && N <= 256 && N % 2 == 0 && (hd == 64 || hd == 128 || hd == 160);
 }
 
+// Optional in-kernel timeline: clock64 stamps of CTA 0's producer / MMA / softmax roles, 16 per work item.
+static long long* g_trace = nullptr;
+static int g_trace_items = 0;
+void attention_set_trace(long long* buf, int items) { g_trace = buf, g_trace_items = items; }
+
 void attention_fwd_persist(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, int B, int N, int H,
                            int hd, cudaStream_t stream) {
     if (!attention_fwd_persist_supported(N, hd))
@@ -338,6 +362,7 @@ void attention_fwd_persist(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat
     p.scale = 1.0f / sqrtf(static_cast<float>(hd));
     p.scale_log2 = p.scale * 1.4426950408889634f;
     p.out = out, p.lse = lse;
+    p.trace = g_trace, p.trace_items = g_trace_items;
     if (hd == 64) launch_persist<64>(q, k, v, p, stream);
     else if (hd == 128) launch_persist<128>(q, k, v, p, stream);
     else launch_persist<160>(q, k, v, p, stream);

@@ -20,6 +20,8 @@ void attention_fwd_long(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16*
 
 // Persistent, software-pipelined forward for 128 < N <= 256 (attention_persist_sm100.cu): out, optional lse.
 bool attention_fwd_persist_supported(int N, int hd);
+// debug: clock64 stamps of CTA 0 (16 int64 slots per work item) written by the persistent forward; nullptr = off
+void attention_set_trace(long long* buf, int items);
 void attention_fwd_persist(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat16* out, float* lse, int B, int N, int H,
                            int hd, cudaStream_t stream);
 

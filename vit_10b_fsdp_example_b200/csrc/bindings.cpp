@@ -122,6 +122,14 @@ bool attention_fwd_persist_supported(int64_t N, int64_t hd) {
     return b200::attention_fwd_persist_supported((int)N, (int)hd);
 }
 
+void attention_set_trace(OptT buf) {
+    if (!buf.has_value()) {
+        b200::attention_set_trace(nullptr, 0);
+        return;
+    }
+    TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous(), "trace: CUDA int64 tensor");
+    b200::attention_set_trace(reinterpret_cast<long long*>(buf->data_ptr()), (int)(buf->numel() / 16));
+}
 void attention_fwd_persist(Tensor qkv, Tensor out, OptT lse, int64_t B, int64_t N, int64_t H, int64_t hd) {
     c10::cuda::CUDAGuard guard(qkv.device());
     TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && out.is_contiguous(), "attention_fwd_persist: bad layouts");
@@ -331,6 +339,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("attention_fwd_supported", &attention_fwd_supported);
     m.def("attention_fwd_long", &attention_fwd_long);
     m.def("attention_fwd_persist", &attention_fwd_persist);
+    m.def("attention_set_trace", &attention_set_trace);
     m.def("attention_fwd_persist_supported", &attention_fwd_persist_supported);
     m.def("attention_bwd", &attention_bwd);
     m.def("attention_bwd_supported", &attention_bwd_supported);

@@ -964,6 +964,11 @@ void layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const __nv_b
         check_launch("layernorm_bwd_small");
         return;
     }
+    static const bool ln_stream = getenv("B200_LN_STREAM") == nullptr || atoi(getenv("B200_LN_STREAM")) != 0;
+    if (ln_stream && layernorm_bwd_stream_supported(D) && rows >= sm_count()) {
+        layernorm_bwd_stream(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, stream);
+        return;
+    }
     const int chunks = (D / 8 + kLnThreads - 1) / kLnThreads;
     const size_t smem = static_cast<size_t>(dxsum != nullptr ? 3 : 2) * D * sizeof(float);
     const int per_sm = std::max<int>(1, std::min<int>(3, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));

@@ -26,6 +26,11 @@ void cross_entropy(const __nv_bfloat16* logits, const int64_t* target, __nv_bflo
 void im2col(const void* img, bool img_is_bf16, __nv_bfloat16* cols, int B, int S, int P, int Kpad,
             cudaStream_t stream);
 
+// Wide-row LayerNorm backward as a cp.async.bulk row pipeline (layernorm_stream.cu); same contract as layernorm_bwd.
+bool layernorm_bwd_stream_supported(int D);
+void layernorm_bwd_stream(const __nv_bfloat16* dy, const __nv_bfloat16* x, const __nv_bfloat16* gamma, const float* mean,
+                          const float* rstd, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                          float* dxsum, int rows, int D, cudaStream_t stream);
 void gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* g, int64_t n, cudaStream_t stream);
 void dgelu_mul(const __nv_bfloat16* dg, const __nv_bfloat16* u, __nv_bfloat16* du, int64_t n, cudaStream_t stream);
 // y = x * keep / (1 - p), keep = Philox-4x32-10(key, vector index): a pure function of (key, position), so recompute and
