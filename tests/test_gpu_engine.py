@@ -143,10 +143,11 @@ def test_lean_blocks_vs_recompute(heads, dim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("heads,dim,img", [(4, 256, 112), (2, 256, 224), (2, 320, 224)])
+@pytest.mark.parametrize("heads,dim,img", [(4, 256, 112), (2, 256, 224), (2, 320, 224), (2, 320, 336)])
 def test_flash_attention_engine_path(heads, dim, img, monkeypatch):
     """Same model, same data: gradients with the flash-style attention pair (lse + fused backward kernels) must
-    match the default path (GEMMs + softmax kernels) to bf16 noise.  Covers N = 64 / 256, hd = 64 / 128 / 160."""
+    match the default path (GEMMs + softmax kernels) to bf16 noise.  Covers N = 64 / 256 / 576 (the 336 px
+    long-sequence kernels), hd = 64 / 128 / 160."""
     from vit_10b_fsdp_example_b200.config import ViTConfig
     from vit_10b_fsdp_example_b200.ops import cuda_ops as co
     from vit_10b_fsdp_example_b200.parallel import FSDPViT

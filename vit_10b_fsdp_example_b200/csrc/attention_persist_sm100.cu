@@ -8,10 +8,17 @@
 //            streamed in 64-key tiles through a 2-stage ring;
 //   warp 1   tcgen05.mma issuer: S = Q K^T (N = 256) for item i+1 is issued right after the PV MMAs of item i, i.e. it
 //            runs under the epilogue of item i;  O += P_j V_j per 64-key tile as soon as that tile of P is staged;
-//   warps 2-5 one thread per query row: row max, exp2, un-normalised bf16 P into a 2-deep shared-memory ring
-//            (K-major SWIZZLE_128B, the A operand of the PV MMA), 1/sum applied in the epilogue, optional log-sum-exp.
+//   warps 2-5 softmax, one thread per query row: row max, exp2, un-normalised bf16 P into a 2-deep shared-memory ring
+//            (K-major SWIZZLE_128B, the A operand of the PV MMA), log-sum-exp; key-column masks are compiled out when
+//            N is a multiple of 64 (ViT-10B: 256);
+//   warps 6-9 epilogue, one thread per query row: O from TMEM x 1/sum -> bf16 -> SWIZZLE_64B staging tile -> TMA store
+//            (coalesced, clipped at the image boundary by the tensor map); it runs under the softmax of the NEXT item.
+// The in-kernel timeline (clock64 stamps, tools/exp_ln_trace.py) of the first version -- softmax and epilogue on the
+// same four warps, per-thread 16-byte global stores -- showed where an item's 16.5 K cycles went: pass 2 (exp2 + pack,
+// masks on every element) 8.4 K, epilogue 4.6 K (32 scattered rows per store instruction), pass 1 1.7 K, waits 1.8 K;
+// tensor pipe and TMA were idle most of the time.  Hence the split roles, the TMA store and the mask-free fast path.
 // TMEM: S [128 x 256] fp32 + O [128 x hd] fp32 (416 columns at hd = 160).  Shared memory: Q 40 KB + K 80 KB +
-// V ring 40 KB + P ring 32 KB = 192 KB at hd = 160.  Scores never reach HBM.
+// V ring 40 KB + P ring 32 KB + O staging 16 KB = 208 KB at hd = 160.  Scores never reach HBM.
 // Replaces timm Attention's materialised softmax (reference run_vit_training.py:134 -> timm Block -> Attention).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -29,7 +36,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int kPThreads = 192;
+constexpr int kPThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax, warps 6-9 epilogue
 constexpr int kVT = 64;    // keys per V / P tile
 constexpr int kNK = 256;   // key columns of the score tile (padded)
 
@@ -63,15 +70,17 @@ struct PersistCfg {
     static constexpr int kVBytes = kVT * HD * 2;
     static constexpr int kEBytes = 128 * kVT * 2;
     static constexpr int kColAcc = kNK;
-    static constexpr int kSmem = kQBytes + kKBytes + 2 * kVBytes + 2 * kEBytes + 256;
+    static constexpr int kOBytes = 128 * 32 * 2;  // output staging tile: 128 rows x 32 columns (SWIZZLE_64B)
+    static constexpr int kSmem = kQBytes + kKBytes + 2 * kVBytes + 2 * kEBytes + 2 * kOBytes + 2 * 128 * 4 + 256;
     static_assert(kNK + HD <= 512, "TMEM budget exceeded");
     static_assert(kSmem <= 232448, "shared memory budget exceeded");
 };
 
-template <int HD>
+template <int HD, bool kMask>
 __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                           const __grid_constant__ CUtensorMap tmap_k,
                                                                           const __grid_constant__ CUtensorMap tmap_v,
+                                                                          const __grid_constant__ CUtensorMap tmap_o,
                                                                           const PersistParams p) {
     using C = PersistCfg<HD>;
     constexpr int W = C::W, kAtoms = C::kAtoms, kRowBytes = C::kRowBytes;
@@ -83,7 +92,9 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
     uint8_t* sK = sQ + C::kQBytes;
     uint8_t* sV = sK + C::kKBytes;               // [2 stages]
     uint8_t* sE = sV + 2 * C::kVBytes;           // [2 buffers]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 2 * C::kEBytes);
+    uint8_t* sO = sE + 2 * C::kEBytes;           // [2 buffers] output staging
+    float* s_inv = reinterpret_cast<float*>(sO + 2 * C::kOBytes);  // [2 items][128 rows] 1 / row sum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * 128);
     uint64_t* qk_full = bars;
     uint64_t* qk_empty = bars + 1;
     uint64_t* s_full = bars + 2;
@@ -94,7 +105,8 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
     uint64_t* v_empty = bars + 8;   // [2]
     uint64_t* e_full = bars + 10;   // [2]
     uint64_t* e_empty = bars + 12;  // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* stat_full = bars + 14;  // [2] softmax -> epilogue: 1/sum of the item's rows is in s_inv
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
     const uint32_t warp_idx = threadIdx.x / 32;
     const uint32_t lane = lane_id();
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_k);
         prefetch_tmap(&tmap_v);
+        prefetch_tmap(&tmap_o);
         mbar_init(qk_full, 1);
         mbar_init(qk_empty, 1);
         mbar_init(s_full, 1);
@@ -124,6 +137,7 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             mbar_init(&v_empty[i], 1);
             mbar_init(&e_full[i], 4);
             mbar_init(&e_empty[i], 1);
+            mbar_init(&stat_full[i], 4);
         }
         fence_mbar_init();
     }
@@ -211,8 +225,8 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
                 umma_commit<1>(acc_full);
             }
         }
-    } else {
-        // ===================================== softmax + epilogue =====================================
+    } else if (warp_idx < 6) {
+        // ===================================== softmax (warps 2-5) =====================================
         const uint32_t quarter = warp_idx & 3;
         const uint32_t r = quarter * 32 + lane;
         const uint32_t taddr = tmem_base + ((quarter * 32) << 16);
@@ -224,91 +238,129 @@ __global__ void __launch_bounds__(kPThreads) attn_fwd_persist_sm100_kernel(const
             mbar_wait(s_full, i & 1);
             if (warp_idx == 2 && lane == 0) stamp(p, i, kTrSFull);
             tc_fence_after();
+            // ---- pass 1: row maximum ----
             float mx = -INFINITY;
-            for (int c = 0; c < nkt * 2; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, v);
+            for (int c = 0; c < nkt; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(taddr + c * 64, v0);
+                tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int x = 0; x < 32; ++x)
-                    if (c * 32 + x < p.N) mx = fmaxf(mx, __uint_as_float(v[x]));
+                for (int x = 0; x < 32; ++x) {
+                    if (!kMask || c * 64 + x < p.N) mx = fmaxf(mx, __uint_as_float(v0[x]));
+                    if (!kMask || c * 64 + 32 + x < p.N) mx = fmaxf(mx, __uint_as_float(v1[x]));
+                }
             }
             const float m_scaled = mx * p.scale_log2;
             float sum = 0.f;
             if (warp_idx == 2 && lane == 0) stamp(p, i, kTrPass1);
+            // ---- pass 2: P = exp2(S * c - m) per 64-key tile -> shared memory ----
             for (int j = 0; j < nkt; ++j) {
                 const int t = i * nkt + j, eb = t & 1;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(taddr + j * kVT, v0);
+                tmem_ld_32x32b_x32(taddr + j * kVT + 32, v1);
                 if (t >= 2) mbar_wait(&e_empty[eb], ((t >> 1) - 1) & 1);
                 const uint32_t erow = smem_u32(sE) + eb * C::kEBytes + r * 128;
+                tmem_ld_wait();
+                uint32_t pk[32];
+                float s0 = 0.f, s1 = 0.f;  // two independent accumulation chains
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + j * kVT + c * 32, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int x = 0; x < 32; x += 2) {
-                        const int col = j * kVT + c * 32 + x;
-                        const float e0 = col < p.N ? exp2f(fmaf(__uint_as_float(v[x]), p.scale_log2, -m_scaled)) : 0.f;
-                        const float e1 = col + 1 < p.N ? exp2f(fmaf(__uint_as_float(v[x + 1]), p.scale_log2, -m_scaled)) : 0.f;
-                        sum += e0 + e1;
-                        pk[x / 2] = pack_bf16x2(e0, e1);
+                for (int x = 0; x < 32; x += 2) {
+                    const int col = j * kVT + x;
+                    float e0 = exp2f(fmaf(__uint_as_float(v0[x]), p.scale_log2, -m_scaled));
+                    float e1 = exp2f(fmaf(__uint_as_float(v0[x + 1]), p.scale_log2, -m_scaled));
+                    float f0 = exp2f(fmaf(__uint_as_float(v1[x]), p.scale_log2, -m_scaled));
+                    float f1 = exp2f(fmaf(__uint_as_float(v1[x + 1]), p.scale_log2, -m_scaled));
+                    if (kMask) {
+                        e0 = col < p.N ? e0 : 0.f;
+                        e1 = col + 1 < p.N ? e1 : 0.f;
+                        f0 = col + 32 < p.N ? f0 : 0.f;
+                        f1 = col + 33 < p.N ? f1 : 0.f;
                     }
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const uint32_t chunk = c * 4 + j8;
-                        st_shared_v4(erow + ((chunk ^ (r & 7)) << 4), pk[j8 * 4], pk[j8 * 4 + 1], pk[j8 * 4 + 2],
-                                     pk[j8 * 4 + 3]);
-                    }
+                    s0 += e0 + e1;
+                    s1 += f0 + f1;
+                    pk[x / 2] = pack_bf16x2(e0, e1);
+                    pk[16 + x / 2] = pack_bf16x2(f0, f1);
                 }
+                sum += s0 + s1;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    st_shared_v4(erow + ((ch ^ (r & 7)) << 4), pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
                 fence_proxy_async_smem();  // generic-proxy P writes -> async-proxy (tensor core) reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&e_full[eb]);
             }
             tc_fence_before();
+            s_inv[(i & 1) * 128 + r] = 1.0f / sum;
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);  // S of the next item may overwrite the score columns
+            if (lane == 0) {
+                mbar_arrive(s_empty);          // S of the next item may overwrite the score columns
+                mbar_arrive(&stat_full[i & 1]);  // the epilogue warps may read this item's 1 / sum
+            }
             if (warp_idx == 2 && lane == 0) stamp(p, i, kTrPass2);
-            const float inv = 1.0f / sum;
             const int64_t bh = static_cast<int64_t>(b) * p.H + h;
             if (p.lse != nullptr && row_ok) p.lse[bh * p.N + q] = mx * p.scale + __logf(sum);
-
+        }
+    } else {
+        // ===================================== epilogue (warps 6-9) =====================================
+        const uint32_t quarter = warp_idx & 3;
+        const uint32_t r = quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16);
+        const uint32_t et = threadIdx.x - 192;
+        uint32_t flip = 0;
+        for (int i = 0; i < n_items; ++i) {
+            int qb, h, b;
+            decode(i, qb, h, b);
+            mbar_wait(&stat_full[i & 1], (i >> 1) & 1);
+            const float inv = s_inv[(i & 1) * 128 + r];
             mbar_wait(acc_full, i & 1);
-            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrAccFull);
+            if (warp_idx == 6 && lane == 0) stamp(p, i, kTrAccFull);
             tc_fence_after();
-            __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.N + q) * p.D + h * HD;
 #pragma unroll 1
             for (int c = 0; c < HD / 32; ++c) {
+                uint8_t* buf = sO + (flip & 1) * C::kOBytes;
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + C::kColAcc + c * 32, v);
+                if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
+                named_bar_sync(2, 128);
                 tmem_ld_wait();
-                if (row_ok) {
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
-                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
-                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
-                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + j8 * 8) = o;
-                    }
+                if (c == HD / 32 - 1) {  // O is in registers: the PV MMAs of the next item may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
                 }
+                // staging tile: [128 rows x 64 B], SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3)
+                const uint32_t orow = smem_u32(buf) + r * 64;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    st_shared_v4(orow + ((j8 ^ ((r >> 1) & 3)) << 4),
+                                 pack_bf16x2(__uint_as_float(v[j8 * 8]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv),
+                                 pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv),
+                                 pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv),
+                                 pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0) {  // rows beyond the image (N not a multiple of 128) are clipped by the tensor map
+                    tma_store_4d(&tmap_o, buf, c * 32, qb * 128, h, b);
+                    tma_store_commit();
+                }
+                ++flip;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);  // the PV MMAs of the next item may overwrite O
-            if (warp_idx == 2 && lane == 0) stamp(p, i, kTrEpiDone);
+            if (warp_idx == 6 && lane == 0) stamp(p, i, kTrEpiDone);
         }
+        if (et == 0) tma_store_wait<0>();
     }
     __syncthreads();
     if (warp_idx == 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int HD>
-void launch_persist(const GemmOperand& q, const GemmOperand& k, const GemmOperand& v, const PersistParams& p,
-                    cudaStream_t stream) {
+template <int HD, bool kMask>
+void launch_persist(const GemmOperand& q, const GemmOperand& k, const GemmOperand& v, const GemmOperand& o,
+                    const PersistParams& p, cudaStream_t stream) {
     using C = PersistCfg<HD>;
-    auto kern = attn_fwd_persist_sm100_kernel<HD>;
+    auto kern = attn_fwd_persist_sm100_kernel<HD, kMask>;
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
@@ -324,8 +376,9 @@ void launch_persist(const GemmOperand& q, const GemmOperand& k, const GemmOperan
     CUtensorMap tq = make_tensor_map_4d(q, HD, p.N, C::W, 128, sw);
     CUtensorMap tk = make_tensor_map_4d(k, HD, p.N, C::W, kNK, sw);
     CUtensorMap tv = make_tensor_map_4d(v, HD, p.N, C::W, kVT, sw);
+    CUtensorMap to = make_tensor_map_4d(o, HD, p.N, 32, 128, 64);  // store box: 32 columns x 128 rows, SWIZZLE_64B
     const int grid = p.total < num_sms ? p.total : num_sms;
-    kern<<<grid, kPThreads, C::kSmem, stream>>>(tq, tk, tv, p);
+    kern<<<grid, kPThreads, C::kSmem, stream>>>(tq, tk, tv, to, p);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess)
         throw std::runtime_error(std::string("attention persist launch: ") + cudaGetErrorString(err));
@@ -363,9 +416,18 @@ void attention_fwd_persist(const __nv_bfloat16* qkv, int64_t ld_qkv, __nv_bfloat
     p.scale_log2 = p.scale * 1.4426950408889634f;
     p.out = out, p.lse = lse;
     p.trace = g_trace, p.trace_items = g_trace_items;
-    if (hd == 64) launch_persist<64>(q, k, v, p, stream);
-    else if (hd == 128) launch_persist<128>(q, k, v, p, stream);
-    else launch_persist<160>(q, k, v, p, stream);
+    GemmOperand o;  // out viewed as [B][H][N rows, hd columns]: what the epilogue's TMA stores address
+    o.ptr = out, o.ld = D;
+    o.nb_inner = H, o.stride_b_inner = hd;
+    o.nb_outer = B, o.stride_b_outer = static_cast<int64_t>(N) * D;
+    const bool mask = N % kVT != 0;  // key columns beyond N exist only in a ragged last tile
+#define B200_PERSIST(HDV)                                                  \
+    if (mask) launch_persist<HDV, true>(q, k, v, o, p, stream);            \
+    else launch_persist<HDV, false>(q, k, v, o, p, stream)
+    if (hd == 64) { B200_PERSIST(64); }
+    else if (hd == 128) { B200_PERSIST(128); }
+    else { B200_PERSIST(160); }
+#undef B200_PERSIST
 }
 
 }  // namespace b200

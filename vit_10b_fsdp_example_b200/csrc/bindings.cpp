@@ -122,6 +122,9 @@ bool attention_fwd_persist_supported(int64_t N, int64_t hd) {
     return b200::attention_fwd_persist_supported((int)N, (int)hd);
 }
 
+bool attention_fwd_long_supported(int64_t N, int64_t hd) {
+    return b200::attention_fwd_long_supported((int)N, (int)hd);
+}
 void attention_set_trace(OptT buf) {
     if (!buf.has_value()) {
         b200::attention_set_trace(nullptr, 0);
@@ -338,6 +341,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("attention_fwd", &attention_fwd);
     m.def("attention_fwd_supported", &attention_fwd_supported);
     m.def("attention_fwd_long", &attention_fwd_long);
+    m.def("attention_fwd_long_supported", &attention_fwd_long_supported);
     m.def("attention_fwd_persist", &attention_fwd_persist);
     m.def("attention_set_trace", &attention_set_trace);
     m.def("attention_fwd_persist_supported", &attention_fwd_persist_supported);
