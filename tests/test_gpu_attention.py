@@ -132,8 +132,12 @@ def test_persistent_attention_backward(B, N, H, hd, monkeypatch):
     dout = torch.randn(B * N, D, device="cuda").to(torch.bfloat16)
     out, lse = co.attention_fwd_lse(qkv, B, N, H, hd)        # one-shot forward (validated)
     monkeypatch.setattr(co, "ATTN_PERSIST", True)
-    dqkv = co.attention_bwd_lse(dout, qkv, out, lse, B, N, H, hd)
+    n0 = co.launch_count()
+    dqkv, cs = co.attention_bwd_lse(dout, qkv, out, lse, B, N, H, hd, want_colsum=True)
+    assert co.launch_count() - n0 == 1, "bias-gradient column sums must come out of the backward kernels themselves"
     dqkvr = to.attention_bwd_lse(dout.float(), qkv.float(), out.float(), lse, B, N, H, hd)
+    csr = dqkv.float().sum(dim=0)  # sums of the bf16 values that were stored
+    assert (cs - csr).abs().max().item() <= 2e-3 * csr.abs().max().item() + 1e-3, "fused qkv bias gradient"
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         got, ref = dqkv[:, sl].float(), dqkvr[:, sl].float()
         err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)

@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kBwdThreads) attn_fwd_long_sm100_kernel(const 
 // delta[bh, q] = sum_d dO[token, h*hd + d] * O[token, h*hd + d]; 4 lanes per (token, head)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
                                   const __nv_bfloat16* __restrict__ out, int64_t ld_o, float* __restrict__ delta,
-                                  int B, int N, int H, int hd) {
+                                  const float* __restrict__ lse, float* __restrict__ lse2, int B, int N, int H, int hd) {
     const int64_t gid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 4;
     const int sub = threadIdx.x & 3;
     const int64_t total = static_cast<int64_t>(B) * N * H;
@@ -662,6 +662,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_
         const int64_t token = gid / H;
         const int64_t bb = token / N, q = token % N;
         delta[(bb * H + hh) * N + q] = acc;
+        // the persistent backward wants the row log-sum-exp in log2 units, bulk-copyable: write it alongside
+        if (lse2 != nullptr) lse2[(bb * H + hh) * N + q] = lse[(bb * H + hh) * N + q] * 1.4426950408889634f;
     }
 }
 
@@ -750,20 +752,24 @@ bool attention_bwd_supported(int N, int hd) {
 
 void attention_bwd(const __nv_bfloat16* qkv, int64_t ld_qkv, const __nv_bfloat16* dout, int64_t ld_do,
                    const __nv_bfloat16* out, int64_t ld_o, const float* lse, float* delta, __nv_bfloat16* dqkv,
-                   int B, int N, int H, int hd, cudaStream_t stream, bool persist) {
+                   int B, int N, int H, int hd, cudaStream_t stream, bool persist, float* colsum) {
     if (!attention_bwd_supported(N, hd)) throw std::runtime_error("attention_bwd: unsupported (N, head_dim)");
     const int D = H * hd;
     {
         const int64_t threads = static_cast<int64_t>(B) * N * H * 4;
+        // persist: `delta` holds two [B*H, N] planes -- delta, then lse * log2(e)
+        float* lse2 = persist ? delta + static_cast<int64_t>(B) * H * N : nullptr;
         attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(dout, ld_do, out, ld_o, delta,
-                                                                                           B, N, H, hd);
+                                                                                           lse, lse2, B, N, H, hd);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) throw std::runtime_error(std::string("attention delta launch: ") + cudaGetErrorString(err));
     }
     if (persist) {
-        attention_bwd_persist_core(qkv, ld_qkv, dout, ld_do, lse, delta, dqkv, B, N, H, hd, stream);
+        attention_bwd_persist_core(qkv, ld_qkv, dout, ld_do, delta + static_cast<int64_t>(B) * H * N, delta, dqkv, colsum,
+                                   B, N, H, hd, stream);
         return;
     }
+    if (colsum != nullptr) throw std::runtime_error("attention_bwd: fused column sums need the persistent kernels");
     GemmOperand q, k, v, dO;
     q.ptr = qkv, k.ptr = qkv + D, v.ptr = qkv + 2 * D, dO.ptr = dout;
     for (GemmOperand* o : {&q, &k, &v, &dO}) {

@@ -133,6 +133,14 @@ void attention_set_trace(OptT buf) {
     TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous(), "trace: CUDA int64 tensor");
     b200::attention_set_trace(reinterpret_cast<long long*>(buf->data_ptr()), (int)(buf->numel() / 16));
 }
+void attention_bwd_set_trace(OptT buf, int64_t role) {
+    if (!buf.has_value()) {
+        b200::attention_bwd_set_trace(nullptr, 0, 0);
+        return;
+    }
+    TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous(), "trace: CUDA int64 tensor");
+    b200::attention_bwd_set_trace(reinterpret_cast<long long*>(buf->data_ptr()), (int)(buf->numel() / 16), (int)role);
+}
 void attention_fwd_persist(Tensor qkv, Tensor out, OptT lse, int64_t B, int64_t N, int64_t H, int64_t hd) {
     c10::cuda::CUDAGuard guard(qkv.device());
     TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && out.is_contiguous(), "attention_fwd_persist: bad layouts");
@@ -142,17 +150,18 @@ void attention_fwd_persist(Tensor qkv, Tensor out, OptT lse, int64_t B, int64_t 
 
 bool attention_bwd_supported(int64_t N, int64_t hd) { return b200::attention_bwd_supported((int)N, (int)hd); }
 
-void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta, Tensor dqkv, int64_t B, int64_t N,
-                   int64_t H, int64_t hd, bool persist) {
+void attention_bwd(Tensor qkv, Tensor dout, Tensor out, Tensor lse, Tensor delta, Tensor dqkv, OptT colsum, int64_t B,
+                   int64_t N, int64_t H, int64_t hd, bool persist) {
     c10::cuda::CUDAGuard guard(qkv.device());
     TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1 && dout.stride(1) == 1 && out.stride(1) == 1 &&
                     dqkv.is_contiguous() && lse.is_contiguous() && delta.is_contiguous(),
                 "attention_bwd: bad layouts");
-    TORCH_CHECK(lse.numel() == B * H * N && delta.numel() == B * H * N && dqkv.size(1) == 3 * H * hd,
-                "attention_bwd: bad shapes");
+    TORCH_CHECK(lse.numel() == B * H * N && delta.numel() == (persist ? 2 : 1) * B * H * N && dqkv.size(1) == 3 * H * hd,
+                "attention_bwd: bad shapes (delta needs two [B*H, N] planes for the persistent kernels)");
+    TORCH_CHECK(!persist || N % 4 == 0, "attention_bwd: persistent kernels need N % 4 == 0");
     b200::attention_bwd(bf16_ptr(qkv), qkv.stride(0), bf16_ptr(dout), dout.stride(0), bf16_ptr(out), out.stride(0),
                         f32_ptr(lse), f32_ptr(delta), bf16_mut(dqkv), (int)B, (int)N, (int)H, (int)hd, cur_stream(),
-                        persist);
+                        persist, colsum.has_value() ? f32_ptr(*colsum) : nullptr);
 }
 
 void cross_entropy(Tensor logits, Tensor target, OptT dlogits, Tensor loss, OptT correct) {
@@ -344,6 +353,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("attention_fwd_long_supported", &attention_fwd_long_supported);
     m.def("attention_fwd_persist", &attention_fwd_persist);
     m.def("attention_set_trace", &attention_set_trace);
+    m.def("attention_bwd_set_trace", &attention_bwd_set_trace);
     m.def("attention_fwd_persist_supported", &attention_fwd_persist_supported);
     m.def("attention_bwd", &attention_bwd);
     m.def("attention_bwd_supported", &attention_bwd_supported);

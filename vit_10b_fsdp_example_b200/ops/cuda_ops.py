@@ -317,9 +317,7 @@ def use_flash(N: int, hd: int) -> bool:
     """Model-level policy: run the attention core through the fused forward (log-sum-exp) + fused backward pair?"""
     if not FLASH_ATTENTION or not flash_supported(N, hd):
         return False
-    if _FLASH_ENV == "1":
-        return True
-    return hd <= 128 or N > 256
+    return True
 
 
 def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
@@ -336,9 +334,15 @@ def attention_fwd_lse(qkv, B: int, N: int, H: int, hd: int):
 
 def attention_bwd_lse(dout, qkv, out, lse, B: int, N: int, H: int, hd: int, want_colsum: bool = False):
     dqkv = torch.empty(B * N, 3 * H * hd, dtype=qkv.dtype, device=qkv.device)
-    delta = torch.empty(B * H, N, dtype=torch.float32, device=qkv.device)
-    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, B, N, H, hd, _persist(hd))
-    return (dqkv, colsum(dqkv)) if want_colsum else dqkv
+    persist = _persist(hd) and N % 4 == 0  # the persistent kernels bulk-copy per-row statistics in 16-byte units
+    # scratch: rowsum(dO o O); the persistent kernels get a second plane holding lse * log2(e)
+    delta = torch.empty(2 if persist else 1, B * H, N, dtype=torch.float32, device=qkv.device)
+    # the persistent kernels reduce the qkv bias gradient (column sums of dq | dk | dv) from their epilogue tiles
+    cs = torch.zeros(3 * H * hd, dtype=torch.float32, device=qkv.device) if (want_colsum and persist) else None
+    _C.attention_bwd(qkv, dout, out, lse, delta, dqkv, cs, B, N, H, hd, persist)
+    if want_colsum and cs is None:
+        cs = colsum(dqkv)
+    return (dqkv, cs) if want_colsum else dqkv
 
 
 def attention_probs(qkv, B: int, N: int, H: int, hd: int):
