@@ -56,7 +56,9 @@ def consolidate_files(ckpt_prefix: str, ckpt_suffix: str = "_rank_*.ckpt", save_
 
     paths = sorted(glob.glob(ckpt_prefix + ckpt_suffix))
     assert paths, f"no checkpoint files match {ckpt_prefix + ckpt_suffix}"
-    ckpts = [torch.load(p, map_location="cpu", weights_only=False) for p in paths]
+    # mmap: only the tensors that are actually copied (the model shards) are paged in -- a ViT-10B rank file also
+    # carries two fp32 AdamW moments per parameter that consolidation never touches
+    ckpts = [torch.load(p, map_location="cpu", weights_only=False, mmap=True) for p in paths]
     full = consolidate(ckpts)
     if save_path:
         os.makedirs(os.path.dirname(os.path.abspath(save_path)), exist_ok=True)
