@@ -4,7 +4,7 @@ import re
 import subprocess
 import sys
 
-OBJS = ["gemm_sm100.cu.o", "attention_sm100.cu.o", "attention_bwd_sm100.cu.o", "attention_persist_sm100.cu.o", "attention_bwd_persist_sm100.cu.o", "comm.cu.o", "elementwise.cu.o"]
+OBJS = ["gemm_sm100.cu.o", "attention_sm100.cu.o", "attention_bwd_sm100.cu.o", "attention_persist_sm100.cu.o", "attention_bwd_persist_sm100.cu.o", "comm.cu.o", "elementwise.cu.o", "layernorm_stream.cu.o"]
 INTEREST = re.compile(r"^(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|UTCCP|SYNCS|MULTIMEM|"
                       r"LDGMC|LDG\.E\.NA|STG\.E\.NA|LDG\.E\.STRONG|STG\.E\.STRONG|LDG\.E\.128|STG\.E\.128|RED|ATOM|MEMBAR|HMMA|UCGABAR)")
 
