@@ -430,7 +430,10 @@ class FSDPViT:
         left = int(0.6 * (free - margin - k * self.lean_bytes_per_block(batch)))
         extras = []
         for name, nbytes in self.extra_bytes_per_block(batch):
-            n = int(max(0, min(k, left // max(1, nbytes)))) if k == len(self.units) and EXTRAS_ENABLED else 0
+            if nbytes <= 0:  # nothing to keep for this slot (P under the fused attention pair)
+                extras.append(0)
+                continue
+            n = int(max(0, min(k, left // nbytes))) if k == len(self.units) and EXTRAS_ENABLED else 0
             left -= n * nbytes
             extras.append(n)
         vals = [k] + extras
@@ -446,8 +449,11 @@ class FSDPViT:
         es = torch.empty((), dtype=self.dtype).element_size()
         unit = batch * cfg.num_patches * cfg.embed_dim * es
         npad = (cfg.num_patches + 7) // 8 * 8
-        return (("P", batch * cfg.num_heads * cfg.num_patches * npad * es), ("h", 2 * unit),
-                ("g", int(cfg.mlp_ratio * unit)))
+        # with the fused attention pair (forward keeps the row log-sum-exp, backward rebuilds P tile by tile) there is
+        # no P to keep: its budget goes to the LayerNorm outputs and gelu(u) instead
+        flash = bool(getattr(self.ops, "use_flash", lambda n, hd: False)(cfg.num_patches, cfg.head_dim))
+        p_bytes = 0 if flash else batch * cfg.num_heads * cfg.num_patches * npad * es
+        return (("P", p_bytes), ("h", 2 * unit), ("g", int(cfg.mlp_ratio * unit)))
 
     def _save_mode(self, i: int, keep_from: int):
         """What block i stores in forward: False = only its input (checkpoint), True = everything
