@@ -54,10 +54,15 @@ def _collectives_worker(rank, world, port, out_path):
         sm.params_updated()
         full_a = torch.zeros(lay.full_numel, dtype=torch.bfloat16, device=dev)
         full_b = torch.zeros(lay.full_numel, dtype=torch.bfloat16, device=dev)
-        sm.all_gather(lay, shard, full_a)
         nc.all_gather(lay, shard, full_b)
-        torch.cuda.synchronize()
-        res[f"ag_exact_{int(flatten)}"] = bool(torch.equal(full_a, full_b))
+        ok_ag = True
+        for transport in ("kernel", "ce"):  # light pull kernel and copy-engine transport of the all-gather
+            sm.ag_transport = transport
+            full_a.zero_()
+            sm.all_gather(lay, shard, full_a)
+            torch.cuda.synchronize()
+            ok_ag = ok_ag and bool(torch.equal(full_a, full_b))
+        res[f"ag_exact_{int(flatten)}"] = ok_ag
         # reduce-scatter: P2P and (if available) NVLS vs NCCL fp32
         grad = sm.alloc_full_grad(lay.full_numel, torch.bfloat16)
         grad.copy_(torch.randn(lay.full_numel, device=dev))

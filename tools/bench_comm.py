@@ -67,8 +67,14 @@ def main():
         grad32 = grad.float()
         out_nccl = torch.empty(lay.shard_numel, dtype=torch.float32, device=dev)
         r = {"world": world, "full_MiB": nbytes / 2 ** 20, "nvls": bool(be.use_nvls)}
-        t = timed(lambda: be.all_gather(lay, shard, full))
-        r["ag_custom_ms"], r["ag_custom_busGBs"] = t, ingress / t / 1e6
+        for transport in ("kernel", "ce"):  # light pull kernel vs copy engines
+            be.ag_transport = transport
+            full.zero_()
+            t = timed(lambda: be.all_gather(lay, shard, full))
+            r[f"ag_{transport}_ms"], r[f"ag_{transport}_busGBs"] = t, ingress / t / 1e6
+            dist.all_gather_into_tensor(full_nccl, shard)
+            torch.cuda.synchronize()
+            r[f"ag_{transport}_exact"] = bool(torch.equal(full.view(world, -1), full_nccl.view(world, -1)))
         t = timed(lambda: dist.all_gather_into_tensor(full_nccl, shard))
         r["ag_nccl_ms"], r["ag_nccl_busGBs"] = t, ingress / t / 1e6
         t = timed(lambda: be.reduce_scatter(lay, grad, out32, sumsq, cuda_ops))

@@ -267,6 +267,19 @@ void p2p_all_gather(std::vector<int64_t> peer_ptrs, int64_t rank, Tensor out, Te
     b200::p2p_all_gather(peer_ptrs, (int)rank, out.data_ptr(), seg_ptr(seg_table), (int)seg_table.size(0),
                          total_chunks, (int)max_ctas, cur_stream());
 }
+// Copy-engine transport of the all-gather: one asynchronous device-to-device copy per (parameter group, source rank)
+// straight from the peer's symmetric shard into its final place in the gathered buffer.  No SM, no shared memory, no
+// registers are taken from the GEMM running next to it, and the DMA engines keep the NVLink pipe full where SM-issued
+// peer loads do not (63 GB/s at W = 4 for the pull kernel, profiles/r2_n4.md).  Graph-capturable (memcpy nodes).
+void ce_all_gather(std::vector<int64_t> src_ptrs, std::vector<int64_t> dst_ptrs, std::vector<int64_t> nbytes) {
+    TORCH_CHECK(src_ptrs.size() == dst_ptrs.size() && src_ptrs.size() == nbytes.size(), "ce_all_gather: ragged lists");
+    cudaStream_t stream = cur_stream();
+    for (size_t i = 0; i < src_ptrs.size(); ++i) {
+        cudaError_t err = cudaMemcpyAsync(reinterpret_cast<void*>(dst_ptrs[i]), reinterpret_cast<const void*>(src_ptrs[i]),
+                                          static_cast<size_t>(nbytes[i]), cudaMemcpyDeviceToDevice, stream);
+        TORCH_CHECK(err == cudaSuccess, "ce_all_gather: ", cudaGetErrorString(err));
+    }
+}
 // adam = [] or (hi, lo, m, v tensors given separately) + hyper = [lr, beta1, beta2, eps, wd, step]
 bool make_adam(const OptT& hi, const OptT& lo, const OptT& m, const OptT& v, const std::vector<double>& hyper,
                b200::AdamFuse& a) {
@@ -372,6 +385,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("merge_fp32", &merge_fp32);
     m.def("clip_coef", &clip_coef);
     m.def("p2p_all_gather", &p2p_all_gather);
+    m.def("ce_all_gather", &ce_all_gather);
     m.def("reduce_scatter", &reduce_scatter);
     m.def("all_reduce_mean", &all_reduce_mean);
     m.def("rs_chunk_vecs", &rs_chunk_vecs);

@@ -124,6 +124,10 @@ class Sm100Backend(TorchDistBackend):
         # Collective kernels are light CTAs (128 threads, <= 96 registers, no shared memory) that run NEXT TO the
         # GEMM CTAs on the same SMs (see csrc/comm.cu); comm_ctas bounds how many SMs host one at a time.
         self.comm_ctas = int(os.environ.get("B200_COMM_CTAS", comm_ctas))
+        # stand-alone all-gather transport: "kernel" = light pull kernel (csrc/comm.cu), "ce" = copy engines.
+        # SM-issued peer loads stop scaling beyond two GPUs on this fabric (305 GB/s at W = 2, 63 GB/s at W = 4) while
+        # DMA peer copies run at 636 GB/s and take nothing from the SMs, so the copy engines are the default.
+        self.ag_transport = os.environ.get("B200_AG_TRANSPORT", "ce")
         self.use_nvls = False
         if world == 1:  # single GPU: nothing to communicate, gathered buffers alias the shards
             return
@@ -191,18 +195,34 @@ class Sm100Backend(TorchDistBackend):
         self._C.signal_barrier(self._flag_ptrs, self.rank, self.world, slot, 0, self._seq_dev)
 
     # ---- segment tables (device int64), built once per (layout, purpose) ----
+    @staticmethod
+    def _lay_key(layout: UnitLayout):
+        """Structural identity of a layout (id() of a short-lived layout object can be recycled by the allocator)."""
+        return (layout.name, layout.world, layout.flatten, layout.full_numel,
+                tuple((g.name, g.full_offset, g.shard_len, g.shard_offset) for g in layout.groups))
+
     def _ag_table(self, layout: UnitLayout, esize: int, exclude=()):
-        key = ("ag", id(layout), esize, tuple(sorted(exclude)))
+        """Segment table of the pull all-gather.  The order of the rows is the order in which this rank's CTAs walk
+        the sources, so it is staggered by rank and rotated every MiB: at any moment the W ranks pull from W
+        *different* peers.  (With every rank walking the sources 0, 1, 2 ... in the same order all of them hit one
+        GPU's egress at once: measured 59 GB/s at W = 4 against 305 GB/s at W = 2, profiles/r2_n4.md.)"""
+        key = ("ag", self._lay_key(layout), esize, tuple(sorted(exclude)))
         if key not in self._seg_cache:
             chunk = self._C.ag_chunk_bytes()
+            piece = 64 * chunk  # 1 MiB per (source, turn)
             rows, prefix = [], 0
+            W = self.world
             for g in layout.groups:
                 if g.name in exclude:
                     continue  # gathered by the GEMM that consumes it (AG fusion)
-                for r in range(self.world):
-                    n = g.shard_len
-                    rows.append([r, g.shard_offset * esize, (g.full_offset + r * n) * esize, n * esize, prefix])
-                    prefix += -(-n * esize // chunk)
+                nbytes = g.shard_len * esize
+                for pi, off in enumerate(range(0, nbytes, piece)):
+                    n = min(piece, nbytes - off)
+                    for k in range(W):
+                        r = (self.rank + k + pi) % W
+                        rows.append([r, g.shard_offset * esize + off, (g.full_offset + r * g.shard_len) * esize + off,
+                                     n, prefix])
+                        prefix += -(-n // chunk)
             self._seg_cache[key] = (torch.tensor(rows, dtype=torch.int64, device=self.device), prefix)
         return self._seg_cache[key]
 
@@ -238,7 +258,7 @@ class Sm100Backend(TorchDistBackend):
                 full_buf.data_ptr() + g.full_offset * esize, flags.data_ptr()] + peers
 
     def _rs_table(self, layout: UnitLayout, esize: int):
-        key = ("rs", id(layout), esize)
+        key = ("rs", self._lay_key(layout), esize)
         if key not in self._seg_cache:
             chunk = self._C.rs_chunk_vecs() * (16 // esize)  # elements per chunk (one CTA pass of 16-byte vectors)
             rows, prefix = [], 0
@@ -252,8 +272,31 @@ class Sm100Backend(TorchDistBackend):
     def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor, exclude=()) -> None:
         if self.world == 1:
             return super().all_gather(layout, shard, out_full)
+        if self.ag_transport == "ce":
+            src, dst, nb = self._ag_copies(layout, shard, out_full, exclude)
+            self._C.ce_all_gather(src, dst, nb)
+            return
         table, chunks = self._ag_table(layout, shard.element_size(), exclude)
         self._C.p2p_all_gather(self._peer[shard.data_ptr()], self.rank, out_full, table, chunks, self.comm_ctas)
+
+    def _ag_copies(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor, exclude=()):
+        """(src, dst, nbytes) lists of the copy-engine all-gather: one copy per (group, source rank), sources walked
+        starting at this rank's successor so the W ranks read from W different peers at any time."""
+        key = ("agce", self._lay_key(layout), shard.data_ptr(), out_full.data_ptr(), tuple(sorted(exclude)))
+        if key not in self._seg_cache:
+            es = shard.element_size()
+            peers = self._peer[shard.data_ptr()]
+            src, dst, nb = [], [], []
+            for k in range(self.world):
+                r = (self.rank + 1 + k) % self.world  # own slice last: it is the only copy that does not need NVLink
+                for g in layout.groups:
+                    if g.name in exclude:
+                        continue
+                    src.append(peers[r] + g.shard_offset * es)
+                    dst.append(out_full.data_ptr() + (g.full_offset + r * g.shard_len) * es)
+                    nb.append(g.shard_len * es)
+            self._seg_cache[key] = (src, dst, nb)
+        return self._seg_cache[key]
 
     supports_fused_adam = True
 

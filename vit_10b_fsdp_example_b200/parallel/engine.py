@@ -126,7 +126,12 @@ class FSDPViT:
         self._sumsq = None
         self._fused_sumsq = False
         self.step_count = 0
-        self.fuse_all_gather = fuse_all_gather and os.environ.get("B200_FUSE_AG", "1") != "0"
+        # All-gather fused into the qkv / fc1 GEMMs (copier warp pulling peer slabs with SM-issued loads): on by default
+        # at W = 2, where peer loads stream at ~300 GB/s; beyond two GPUs SM-issued peer loads drop to ~60 GB/s on this
+        # fabric (profiles/r2_n4.md) and the GEMM would wait for its weights, so the whole block is gathered by the
+        # copy engines instead.  B200_FUSE_AG=1 / 0 forces either way.
+        fuse_env = os.environ.get("B200_FUSE_AG", "")
+        self.fuse_all_gather = fuse_all_gather and fuse_env != "0" and (world <= 2 or fuse_env == "1")
         self._stall_probe = None  # list of (event, event) pairs while exposed_comm_probe() is active
         self._unrecorded = set()  # ids of events created but never recorded (must not be waited on during capture)
         self._fused_opt = None  # ShardedAdamW registered for reduce-scatter + AdamW fusion (clipping off only)
