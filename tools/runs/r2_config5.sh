@@ -3,7 +3,7 @@
 # product CLI (run_vit_training.py), ViT-10B on N GPUs.     gpurun --gpus 4 --timeout 1500 -- 'bash tools/runs/r2_config5.sh 4'
 N=${1:-4}; HALF=$((N / 2)); [ $HALF -lt 1 ] && HALF=1
 EXTRA=${C5_EXTRA:-}            # e.g. tiny dims for a CPU dry run
-CK=${C5_DIR:-/tmp/ck5}; OUT=${C5_OUT:-gpurun_out}
+CK=${C5_DIR:-/dev/shm/ck5}; OUT=${C5_OUT:-gpurun_out}
 mkdir -p $OUT; L=$OUT/r2_config5.log; : > $L; rm -rf $CK
 BS=$((128 * N))
 tr() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((20000 + RANDOM % 20000)) run_vit_training.py --fake_data --log_step_interval 1 --ckpt_dir $CK --test_epoch_interval 100 --warmup_steps 20 $EXTRA "$@"; }
