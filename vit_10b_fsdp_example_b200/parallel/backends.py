@@ -272,7 +272,9 @@ class Sm100Backend(TorchDistBackend):
     def all_gather(self, layout: UnitLayout, shard: torch.Tensor, out_full: torch.Tensor, exclude=()) -> None:
         if self.world == 1:
             return super().all_gather(layout, shard, out_full)
-        if self.ag_transport == "ce":
+        # (inside a CUDA-graph capture the pull kernel is used: it is the transport the graphed multi-GPU step was
+        # validated with; memcpy nodes between peer-mapped allocations are untested there)
+        if self.ag_transport == "ce" and not torch.cuda.is_current_stream_capturing():
             src, dst, nb = self._ag_copies(layout, shard, out_full, exclude)
             self._C.ce_all_gather(src, dst, nb)
             return
