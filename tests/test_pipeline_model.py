@@ -53,3 +53,19 @@ def test_injected_faults_are_detected(bug, args):
         except pm.ProtocolError:
             caught += 1
     assert caught > 0, f"fault {bug} was never detected"
+
+
+def test_forward_softmax_to_epilogue_handoff_needs_its_mbarrier():
+    """Round-2 forward: 1 / row sum travels from the softmax warps to the separate epilogue warps through a plain
+    shared-memory slot ordered only by the stat_full mbarrier (the pair compute-sanitizer racecheck flags, see
+    profiles/r2_sanitizer.md).  With the wait the protocol holds for every schedule; without it the model must see
+    the epilogue read a slot that is stale or half written."""
+    for seed in range(120):
+        pm.model_fwd_persist(seed, 5, 4)
+    caught = 0
+    for seed in range(60):
+        try:
+            pm.model_fwd_persist(seed, 5, 4, bug="no_stat_full")
+        except pm.ProtocolError:
+            caught += 1
+    assert caught == 60

@@ -294,7 +294,12 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
 # ---------------------------------------------------------------------------------------------------------------
 # attention_persist_sm100.cu: persistent forward
 # ---------------------------------------------------------------------------------------------------------------
-def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4):
+def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4, bug: str = ""):
+    """Round-2 kernel: 4 softmax warps (row max, exp2, P ring, 1/sum into s_inv[item & 1]) and 4 separate epilogue
+    warps (wait stat_full[item & 1] -> read s_inv -> wait acc_full -> read O -> arrive acc_empty).  The s_inv slot is a
+    plain shared-memory hand-off between generic-proxy threads ordered ONLY by the stat_full mbarrier -- the pair
+    compute-sanitizer racecheck reports (profiles/r2_sanitizer.md).  bug="no_stat_full" drops that wait (the model must
+    then see the epilogue read a stale / half-written slot); bug="stat_single" uses one slot instead of two."""
     s = Sim(seed)
     W = warps
     qk_full, qk_empty = s.bar("qk_full", 1), s.bar("qk_empty", 1)
@@ -304,11 +309,14 @@ def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4):
     v_empty = [s.bar(f"v_empty{i}", 1) for i in range(2)]
     e_full = [s.bar(f"e_full{i}", W) for i in range(2)]
     e_empty = [s.bar(f"e_empty{i}", 1) for i in range(2)]
+    stat_full = [s.bar(f"stat_full{i}", W) for i in range(2)]
     QK = s.buf("QK")
     V = [s.buf(f"V{i}") for i in range(2)]
     E = [s.buf(f"E{i}", W) for i in range(2)]
     S = s.buf("S", W)
     ACC = s.buf("O", W)
+    SINV = [s.buf(f"s_inv{i}", W) for i in range(2)]
+    slot = (lambda i: 0) if bug == "stat_single" else (lambda i: i & 1)
 
     def producer():
         def load_v(i, j):
@@ -352,7 +360,7 @@ def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4):
     def softmax(w):
         for i in range(n_items):
             yield ("wait", s_full, i & 1)
-            yield ("read", S, i + 1)  # pass A (row max) and pass B read the same version
+            yield ("read", S, i + 1)  # pass 1 (row max) and pass 2 read the same version
             for j in range(nkt):
                 t = i * nkt + j
                 eb = t & 1
@@ -361,7 +369,20 @@ def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4):
                 S.check_readable(f"softmax{w}", i + 1)
                 yield ("write_part", E[eb])
                 yield ("arrive", e_full[eb])
+            # 1 / row sum for the epilogue warps: every epilogue warp must have read the slot's previous contents
+            sl = SINV[slot(i)]
+            if sl.parts == 0 and sl.version > 0 and sl.sync_reads.get(sl.version, 0) < W:
+                raise ProtocolError(f"softmax{w}: {sl.name} v{sl.version} overwritten before every epilogue warp read it")
+            yield ("write_part", sl)
             yield ("arrive", s_empty)
+            yield ("arrive", stat_full[slot(i)])
+
+    def epilogue(w):
+        for i in range(n_items):
+            k = i if bug == "stat_single" else (i >> 1)
+            if bug != "no_stat_full":
+                yield ("wait", stat_full[slot(i)], k & 1)
+            yield ("read", SINV[slot(i)], k + 1)
             yield ("wait", acc_full, i & 1)
             yield ("read", ACC, i + 1)
             yield ("arrive", acc_empty)
@@ -370,6 +391,7 @@ def model_fwd_persist(seed: int, n_items: int, nkt: int, warps: int = 4):
     s.threads["mma"] = mma()
     for w in range(W):
         s.threads[f"softmax{w}"] = softmax(w)
+        s.threads[f"epilogue{w}"] = epilogue(w)
     s.run()
     return s
 
@@ -458,6 +480,6 @@ if __name__ == "__main__":
         model_bwd(seed, 1, 4, 2, 4, False, False)
         model_bwd(seed, 3, 4, 2, 8, True, True)
         model_bwd(seed, 3, 3, 2, 8, False, True)
-        model_fwd_persist(seed, 3, 4)
+        model_fwd_persist(seed, 3, 4)  # softmax + separate epilogue warps (round-2 kernel)
         model_fwd_long(seed, 9)
     print("all protocols passed 200 schedules each")
