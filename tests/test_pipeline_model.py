@@ -69,3 +69,12 @@ def test_forward_softmax_to_epilogue_handoff_needs_its_mbarrier():
         except pm.ProtocolError:
             caught += 1
     assert caught == 60
+
+
+def test_statistics_stage_of_the_persistent_backward():
+    """Round-2 dK/dV role: per-query statistics arrive as bulk copies into a 2-stage buffer.  The model holds with the
+    stat_empty wait and -- like acc_empty -- also without it: a stage is only re-requested after x_empty of the next
+    item, which every softmax warp can only enable after it has left the previous item (belt-and-braces wait)."""
+    for seed in range(60):
+        pm.model_bwd(seed, 5, 3, 2, 8, True, persistent=True)
+        pm.model_bwd(seed, 5, 1, 2, 8, True, persistent=True, bug="no_stat_empty")

@@ -178,7 +178,7 @@ class Sim:
 # ---------------------------------------------------------------------------------------------------------------
 def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bool, persistent: bool, bug: str = ""):
     """n_items must be 1 for the one-shot kernel.  `bug` injects a known protocol fault (used by the tests to show
-    that the checker is sensitive): "no_x_empty", "y_empty_parity", "no_e_empty", "no_ts_empty" (and "no_acc_empty", which the
+    that the checker is sensitive): "no_x_empty", "y_empty_parity", "no_e_empty", "no_ts_empty" (and "no_acc_empty" / "no_stat_empty", which the
     model shows to be harmless: the accumulation of the next item already waits for d_full, which every warp only
     signals after its epilogue -- acc_empty and tp_empty are belt-and-braces waits)."""
     s = Sim(seed)
@@ -192,6 +192,12 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
     e_full, e_empty = s.bar("e_full", W), s.bar("e_empty", 1)
     d_full, d_empty = s.bar("d_full", W), s.bar("d_empty", 1)
     acc_full, acc_empty = s.bar("acc_full", 1), s.bar("acc_empty", W)
+    # round 2, dK/dV role of the persistent kernel: the item's per-query statistics (lse2 | delta) are two 1-D bulk
+    # copies into a 2-stage shared-memory buffer, requested together with the resident tiles
+    stats = persistent and kT
+    stat_full = [s.bar(f"stat_full{i}", 1) for i in range(2)]
+    stat_empty = [s.bar(f"stat_empty{i}", W) for i in range(2)]
+    STAT = [s.buf(f"stat{i}", W) for i in range(2)]
     X = s.buf("X")
     Y = [s.buf(f"Y{i}") for i in range(2)]
     Ts = [s.buf(f"Ts{i}", W) for i in range(2)]
@@ -200,7 +206,15 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
     ACC = s.buf("acc", W)
     T = n_items * nt
 
+    def load_stats(i):
+        if stats:
+            sg = i & 1
+            if i >= 2 and bug != "no_stat_empty":
+                yield ("wait", stat_empty[sg], ((i >> 1) - 1) & 1)
+            yield ("tma", STAT[sg], stat_full[sg])
+
     def producer():
+        yield from load_stats(0)
         yield ("tma", X, x_full)
         for t in range(T):
             i, j = divmod(t, nt)
@@ -211,6 +225,7 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
             if persistent and j == nt - 1 and i + 1 < n_items:
                 if bug != "no_x_empty":
                     yield ("wait", x_empty, i & 1)
+                yield from load_stats(i + 1)
                 yield ("tma", X, x_full)
 
     def mma():
@@ -259,10 +274,14 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
 
     def softmax(w):
         for i in range(n_items):
+            if stats:
+                yield ("wait", stat_full[i & 1], (i >> 1) & 1)
             for j in range(nt):
                 t = i * nt + j
                 tb = t % ts_bufs
                 yield ("wait", ts_full[tb], (t // ts_bufs) & 1)
+                if stats:  # lse2 / delta of this tile's columns come out of the item's statistics stage
+                    STAT[i & 1].check_readable(f"softmax{w}", (i >> 1) + 1)
                 if kT and t > 0 and bug != "no_e_empty":
                     yield ("wait", e_empty, (t - 1) & 1)
                 yield ("read", Ts[tb], t // ts_bufs + 1)
@@ -278,6 +297,9 @@ def model_bwd(seed: int, n_items: int, nt: int, ts_bufs: int, warps: int, kT: bo
                 yield ("write_part", D)
                 yield ("arrive", tp_empty)
                 yield ("arrive", d_full)
+            if stats:
+                yield ("read", STAT[i & 1], (i >> 1) + 1)
+                yield ("arrive", stat_empty[i & 1])
             yield ("wait", acc_full, i & 1)
             yield ("read", ACC, i + 1)
             if persistent:
