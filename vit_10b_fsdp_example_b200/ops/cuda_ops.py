@@ -25,7 +25,7 @@ from typing import Optional
 
 import torch
 
-from . import native, torch_ops
+from . import native
 
 NAME = "sm100"
 
