@@ -30,6 +30,7 @@ class TorchDistBackend:
     def __init__(self, world: int, rank: int, device: torch.device):
         self.world, self.rank, self.device = world, rank, device
         self.is_gloo = world > 1 and dist.get_backend() == "gloo"
+        self._staging = {}
 
     # ---- allocation (plain device memory) ----
     def alloc_shard(self, numel: int, dtype) -> torch.Tensor:
@@ -65,7 +66,13 @@ class TorchDistBackend:
             if out_shard.data_ptr() != full_grad.data_ptr():
                 out_shard.copy_(full_grad[: out_shard.numel()])
         else:
-            staging = torch.empty(W, layout.shard_numel, dtype=torch.float32, device=full_grad.device)
+            # one fp32 staging buffer per shard size, reused across calls (collectives on one stream are serialised, so
+            # the previous user is done): the NCCL / gloo backend is the honest baseline, not a handicapped one
+            key = (layout.shard_numel, str(full_grad.device))
+            staging = self._staging.get(key)
+            if staging is None:
+                staging = self._staging[key] = torch.empty(W, layout.shard_numel, dtype=torch.float32,
+                                                           device=full_grad.device)
             for g in layout.groups:  # copy-in, fp32 so the reduction accumulates in fp32
                 staging[:, g.shard_offset: g.shard_offset + g.shard_len].copy_(
                     full_grad[g.full_offset: g.full_offset + W * g.shard_len].view(W, g.shard_len))
