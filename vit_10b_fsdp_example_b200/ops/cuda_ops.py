@@ -178,13 +178,13 @@ def linear_dgrad(dy, w, dgelu_preact=None, want_colsum: bool = False):
     return (dx, cs) if want_colsum else dx
 
 
-def linear_wgrad(dy, x, out=None):
+def linear_wgrad(dy, x, out=None, block_n: int = 0):
     T, N = dy.shape
     K = x.shape[1]
     dy, x = _tma_rows(dy), _tma_rows(x)
     if out is None:
         out = torch.empty(N, K, dtype=dy.dtype, device=dy.device)
-    gemm_raw(dy, _ld(dy), 1, x, _ld(x), 1, out, _ld(out), N, K, T)
+    gemm_raw(dy, _ld(dy), 1, x, _ld(x), 1, out, _ld(out), N, K, T, block_n=block_n)
     return out
 
 
