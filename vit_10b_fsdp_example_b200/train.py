@@ -195,8 +195,10 @@ class Trainer:
         self.time_meter = SmoothedValue(window_size=5)
 
     def _ckpt_path(self, epoch: int) -> str:
-        # files are keyed by the host-local ordinal, like the reference (:220,247,298)
-        return os.path.join(self.cfg.ckpt_dir, f"epoch_{epoch}_rank_{self.rt.local_rank}.ckpt")
+        # One file per *global* rank.  The reference keys the files by the host-local ordinal (:220,247,298), which is
+        # the same thing on one host but makes the hosts of a pod overwrite each other on a shared file system and
+        # leaves the consolidation tool without ranks >= 8; the global rank is identical on one box and right on many.
+        return os.path.join(self.cfg.ckpt_dir, f"epoch_{epoch}_rank_{self.rt.rank}.ckpt")
 
     # ---- logging: runs as a step closure, i.e. after the step's device work has been enqueued ----
     def _log(self, epoch: int, step: int, loss: torch.Tensor, lr: float, step_ms: float) -> None:
