@@ -90,3 +90,23 @@ def test_activation_policy_has_no_budget_for_p_under_fused_attention(monkeypatch
     assert sizes["P"] > 0 and sizes["h"] > 0 and sizes["g"] > 0
     monkeypatch.setattr(torch_ops, "FLASH_ATTENTION", True)
     assert dict(model.extra_bytes_per_block(4))["P"] == 0
+
+
+def test_keep_policy_is_sized_after_the_first_step_of_this_process_even_when_resumed(monkeypatch):
+    """A resumed run restores step_count > 0 (it seeds the dropout masks) but has not seen its transient memory peak
+    yet: the automatic keep policy must still run its first step fully checkpointed and size itself afterwards."""
+    from helpers import tiny_cfg
+    from vit_10b_fsdp_example_b200.parallel import FSDPViT
+
+    cfg = tiny_cfg()
+    model = FSDPViT(cfg, dtype=torch.float32, seed=1, ckpt_keep_blocks=-1)
+    model.load_state_dict(model.state_dict(), shard_metadata=dict(model.get_shard_metadata(), step_count=7))
+    assert model.step_count == 7 and model.keep_blocks == -1
+    calls = []
+    monkeypatch.setattr(model, "_auto_keep_blocks", lambda batch: calls.append(batch) or 1)
+    x = torch.zeros(2, 3, cfg.image_size, cfg.image_size)
+    y = torch.zeros(2, dtype=torch.long)
+    model.forward_backward(x, y)
+    assert calls == [] and model.keep_blocks == -1 and model.step_count == 8
+    model.forward_backward(x, y)
+    assert calls == [2] and model.keep_blocks == 1

@@ -125,7 +125,8 @@ class FSDPViT:
         self._grad_norm = None
         self._sumsq = None
         self._fused_sumsq = False
-        self.step_count = 0
+        self.step_count = 0        # optimizer steps since the start of training (checkpointed: seeds the dropout masks)
+        self._steps_here = 0       # forward_backward calls of THIS process (the keep policy is sized after the first one)
         # All-gather fused into the qkv / fc1 GEMMs (copier warp pulling peer slabs with SM-issued loads): on by default
         # at W = 2, where peer loads stream at ~300 GB/s; beyond two GPUs SM-issued peer loads drop to ~60 GB/s on this
         # fabric (profiles/r2_n4.md) and the GEMM would wait for its weights, so the whole block is gathered by the
@@ -476,7 +477,8 @@ class FSDPViT:
         B = images.shape[0]
         blocks = self.units
         if self.keep_blocks < 0:
-            if self.step_count == 0 or (self.is_cuda and torch.cuda.is_current_stream_capturing()):
+            # (not step_count: a resumed run starts with step_count > 0 but has not seen its transient peak yet)
+            if self._steps_here == 0 or (self.is_cuda and torch.cuda.is_current_stream_capturing()):
                 n_keep = 0
             else:
                 self.keep_blocks = n_keep = self._auto_keep_blocks(B)
@@ -544,6 +546,7 @@ class FSDPViT:
             self._wait(u.reduce_event)
             u.reduce_event = None
         self.step_count += 1
+        self._steps_here += 1
         return loss
 
     # ------------------------------------------------------------------------------------------------
