@@ -9,19 +9,22 @@ INTEREST = re.compile(r"^(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBA
                       r"LDGMC|LDG\.E\.NA|STG\.E\.NA|LDG\.E\.STRONG|STG\.E\.STRONG|LDG\.E\.128|STG\.E\.128|RED|ATOM|MEMBAR|HMMA|UCGABAR)")
 
 
-def main(build_dir, out):
-    lines = ["# SASS census of the hand-written kernels (cuobjdump -sass, sm_100a)", "",
-             "`UTCHMMA` = tcgen05.mma, `UTMALDG/UTMASTG` = TMA tensor load/store, `LDTM` = tcgen05.ld, `UTCBAR` = "
-             "tcgen05.commit, `UTCATOMSWS` = TMEM alloc, `SYNCS.*` = mbarrier, `LDGMC...HPADD` = multimem.ld_reduce (NVLS in-switch reduce), `LDG.E.NA.128` = streaming peer loads, `*.STRONG.SYS` = cross-GPU flags.", ""]
-    for obj in OBJS:
+def census(build_dir, objs=None):
+    """{object file: {demangled kernel name: Counter(mnemonic -> count)}} for the mnemonics of interest."""
+    out = collections.OrderedDict()
+    for obj in objs or OBJS:
         txt = subprocess.run(["cuobjdump", "-sass", f"{build_dir}/{obj}"], capture_output=True, text=True).stdout
+        mangled = re.findall(r"Function : (\S+)", txt)
+        names = subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.split("\n")
+        pretty = {}
+        for m, n in zip(mangled, names):
+            n = re.sub(r"\(anonymous namespace\)::", "", n.strip())
+            pretty[m] = re.sub(r"\(.*", "", n)
         fn, counts = None, collections.OrderedDict()
         for ln in txt.splitlines():
             m = re.search(r"Function : (\S+)", ln)
             if m:
-                fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-                fn = re.sub(r"\(anonymous namespace\)::", "", fn)
-                fn = re.sub(r"\(.*", "", fn)
+                fn = pretty[m.group(1)]
                 counts[fn] = collections.Counter()
                 continue
             m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", ln)
@@ -29,6 +32,15 @@ def main(build_dir, out):
                 op = m.group(1)
                 if INTEREST.match(op):
                     counts[fn][op] += 1
+        out[obj] = counts
+    return out
+
+
+def main(build_dir, out):
+    lines = ["# SASS census of the hand-written kernels (cuobjdump -sass, sm_100a)", "",
+             "`UTCHMMA` = tcgen05.mma, `UTMALDG/UTMASTG` = TMA tensor load/store, `LDTM` = tcgen05.ld, `UTCBAR` = "
+             "tcgen05.commit, `UTCATOMSWS` = TMEM alloc, `SYNCS.*` = mbarrier, `LDGMC...HPADD` = multimem.ld_reduce (NVLS in-switch reduce), `LDG.E.NA.128` = streaming peer loads, `*.STRONG.SYS` = cross-GPU flags.", ""]
+    for obj, counts in census(build_dir).items():
         lines.append(f"## {obj}")
         lines.append("")
         for fn, c in counts.items():
