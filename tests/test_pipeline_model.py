@@ -78,3 +78,30 @@ def test_statistics_stage_of_the_persistent_backward():
     for seed in range(60):
         pm.model_bwd(seed, 5, 3, 2, 8, True, persistent=True)
         pm.model_bwd(seed, 5, 1, 2, 8, True, persistent=True, bug="no_stat_empty")
+
+
+@pytest.mark.parametrize("tiles,clusters,num_kb,stages,epi_warps", [
+    (7, 2, 3, 3, 8),     # the kernel's shape: 8 epilogue warps per CTA, 20 consumers per CLC response
+    (5, 3, 2, 2, 2),
+    (1, 1, 1, 3, 2),     # a single tile: no CLC response is ever a valid tile
+    (2, 3, 5, 2, 2),     # more resident clusters than tiles
+    (12, 2, 1, 2, 2),    # short K (attention GEMMs): the epilogue, not the MMA, sets the pace
+])
+def test_gemm_cta_pair_clc_protocol(tiles, clusters, num_kb, stages, epi_warps):
+    """gemm_sm100.cu: TMA producers of both CTAs signalling the leader's barrier, multicast commits, double-buffered
+    TMEM accumulator, cluster-launch-control work stealing with multicast responses."""
+    for seed in range(25):
+        pm.model_gemm(seed, tiles, clusters, num_kb, stages, epi_warps=epi_warps, epi_delay=40)
+        pm.model_gemm(seed, tiles, clusters, num_kb, stages, epi_warps=epi_warps, use_clc=False)  # static persistent grid
+
+
+@pytest.mark.parametrize("bug", ["no_empty", "no_tmem_empty", "no_clc_empty", "peer_arms_too"])
+def test_gemm_injected_faults_are_detected(bug):
+    caught = 0
+    for seed in range(40):
+        try:
+            pm.model_gemm(seed, 9, clusters=2, num_kb=1 if bug == "no_tmem_empty" else 3, stages=2, epi_warps=2,
+                          epi_delay=200, bug=bug)
+        except pm.ProtocolError:
+            caught += 1
+    assert caught > 0, f"fault {bug} was never detected"

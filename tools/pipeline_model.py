@@ -1,4 +1,4 @@
-"""Protocol model of the warp-specialised attention kernels (CPU, no GPU needed).
+"""Protocol model of the warp-specialised kernels: attention pipelines and the CTA-pair GEMM (CPU, no GPU needed).
 
 The fused attention kernels are mbarrier pipelines between three kinds of actors: one TMA-producer thread, one
 tcgen05.mma-issuer thread and 4 or 8 softmax warps.  A wrong phase parity does not necessarily hang: an mbarrier
@@ -495,6 +495,275 @@ def model_fwd_long(seed: int, nt: int, warps: int = 4):
     return s
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# gemm_sm100.cu: CTA-pair tcgen05 GEMM with cluster-launch-control (CLC) work stealing
+# ---------------------------------------------------------------------------------------------------------------
+class TxBar(Bar):
+    """mbarrier with a transaction count: the phase completes when all arrivals are in AND the tx-count is zero
+    (complete_tx may land before the matching expect_tx: the count is transiently negative, which is legal)."""
+
+    def __init__(self, name: str, count: int):
+        super().__init__(name, count)
+        self.tx = 0
+
+    def _check(self):
+        if self.pending == self.count and self.tx == 0:
+            self.pending, self.phase = 0, self.phase + 1
+
+    def arrive(self):
+        self.pending += 1
+        if self.pending > self.count:
+            raise ProtocolError(f"{self.name}: more arrivals than the barrier expects in one phase")
+        self._check()
+
+    def expect_tx(self, n: int):
+        self.tx += n
+        self.arrive()
+
+    def complete_tx(self, n: int):
+        self.tx -= n
+        self._check()
+
+
+def model_gemm(seed: int, tiles: int, clusters: int = 2, num_kb: int = 3, stages: int = 3, clc_stages: int = 2,
+               use_clc: bool = True, epi_warps: int = 8, epi_delay: int = 0, bug: str = ""):
+    """`clusters` resident CTA pairs work through `tiles` output tiles.  Per pair: two TMA producers (one per CTA, both
+    signalling the LEADER's full barrier, armed by the leader alone for the bytes of both), one MMA issuer (leader;
+    its commits are multicast to both CTAs), one CLC scheduler (leader; responses multicast to both CTAs, 20
+    consumers per response), 2 x `epi_warps` epilogue warps draining a double-buffered TMEM accumulator.
+
+    Checked: liveness; every MMA reads the k-block it expects in BOTH CTAs' stages; every epilogue warp reads the
+    accumulator of the tile it believes it is working on; nothing is overwritten while in use; all consumers of a pair
+    walk the same tile sequence; every tile is computed exactly once.  bug = "no_empty" | "no_tmem_empty" |
+    "no_clc_empty" | "peer_arms_too" (sensitivity of the checker).  epi_delay = idle scheduling slots an epilogue warp
+    spends between learning that its accumulator is complete and reading it (real epilogues are slow; a uniformly random
+    scheduler would otherwise almost never let the MMA issuer get two tiles ahead of them)."""
+    s = Sim(seed)
+    S_BYTES = 1  # bytes of one CTA's stage, in arbitrary units
+    state = {"next": clusters}  # tiles 0 .. clusters-1 are the resident clusters' own; the rest are cancelled in order
+    done_tiles: Dict[int, int] = {}
+    n_consumers = 2 + 1 + 1 + 2 * epi_warps  # producers, MMA, scheduler, epilogue warps (= 20 in the kernel)
+
+    def add_tag(buf):
+        buf.tag = None
+        return buf
+
+    def build(cl):
+        pre = f"c{cl}."
+        full = [TxBar(pre + f"full{i}", 1) for i in range(stages)]
+        empty = [[s.bar(pre + f"empty{c}_{i}", 1) for i in range(stages)] for c in range(2)]
+        tmem_full = [[s.bar(pre + f"tmem_full{c}_{i}", 1) for i in range(2)] for c in range(2)]
+        tmem_empty = [s.bar(pre + f"tmem_empty{i}", 2 * epi_warps) for i in range(2)]
+        clc_full = [[TxBar(pre + f"clc_full{c}_{i}", 1) for i in range(clc_stages)] for c in range(2)]
+        clc_empty = [s.bar(pre + f"clc_empty{i}", n_consumers) for i in range(clc_stages)]
+        smem = [[add_tag(s.buf(pre + f"smem{c}_{i}")) for i in range(stages)] for c in range(2)]
+        acc = [add_tag(s.buf(pre + f"acc{i}", 2 * epi_warps)) for i in range(2)]
+        resp = [[add_tag(s.buf(pre + f"resp{c}_{i}", 1)) for i in range(clc_stages)] for c in range(2)]
+        for row in clc_full:
+            for b in row:
+                s.bars[b.name] = b
+        for b in full:
+            s.bars[b.name] = b
+
+        class TileIter:
+            def __init__(self):
+                self.tile, self.stage, self.phase, self.n = cl, 0, 0, 0
+
+        def tile_next(it, c, who, arrive=True, full=clc_full, empty_=clc_empty, resp=resp, cl=cl):
+            """generator: the consumer side of one CLC response; sets it.tile / returns validity in it.more"""
+            if not use_clc:
+                it.tile += clusters
+                it.more = it.tile < tiles
+                return
+            yield ("wait", full[c][it.stage], it.phase)
+            r = resp[c][it.stage]
+            if r.write_pending:
+                raise ProtocolError(f"{who}: CLC response slot {r.name} read while the hardware is writing it")
+            if r.version != it.n // clc_stages + 1:  # it.n-th response overall = (it.n // stages + 1)-th use of this slot
+                raise ProtocolError(f"{who}: CLC response slot {r.name} holds its response #{r.version}, expected "
+                                    f"#{it.n // clc_stages + 1} (overwritten before it was consumed, or read early)")
+            val = r.tag
+            r.sync_reads[r.version] = r.sync_reads.get(r.version, 0) + 1
+            if arrive:
+                yield ("arrive", empty_[it.stage])
+            it.stage = 0 if it.stage + 1 == clc_stages else it.stage + 1
+            it.phase ^= 1 if it.stage == 0 else 0
+            it.n += 1
+            it.more = val is not None
+            if it.more:
+                it.tile = val
+
+        def producer(c, full=full, empty=empty, smem=smem, pre=pre):
+            who = pre + f"producer{c}"
+            it = TileIter()
+            stage = phase = 0
+            it.more = it.tile < tiles
+            while it.more:
+                for kb in range(num_kb):
+                    if bug != "no_empty":
+                        yield ("wait", empty[c][stage], phase ^ 1)
+                    yield ("gemm_tma", smem[c][stage], full[stage], S_BYTES, (it.tile, kb), who)
+                    if c == 0 or bug == "peer_arms_too":
+                        yield ("expect_tx", full[stage], 2 * S_BYTES)
+                    stage = 0 if stage + 1 == stages else stage + 1
+                    phase ^= 1 if stage == 0 else 0
+                yield from tile_next(it, c, who)
+
+        def mma(full=full, empty=empty, smem=smem, acc=acc, tmem_full=tmem_full, tmem_empty=tmem_empty, pre=pre):
+            who = pre + "mma"
+            it = TileIter()
+            stage = phase = 0
+            n = 0
+            it.more = it.tile < tiles
+            while it.more:
+                a, aphase = n & 1, (n >> 1) & 1
+                if bug != "no_tmem_empty":
+                    yield ("wait", tmem_empty[a], aphase ^ 1)
+                for kb in range(num_kb):
+                    yield ("wait", full[stage], phase)
+                    yield ("gemm_mma", [smem[0][stage], smem[1][stage]], (it.tile, kb), acc[a], kb == 0, who)
+                    yield ("commit2", [empty[0][stage], empty[1][stage]])
+                    if kb == num_kb - 1:
+                        yield ("commit2", [tmem_full[0][a], tmem_full[1][a]])
+                    stage = 0 if stage + 1 == stages else stage + 1
+                    phase ^= 1 if stage == 0 else 0
+                n += 1
+                yield from tile_next(it, 0, who)
+            if n > 0:  # drain: every epilogue warp of both CTAs released the last accumulators
+                last = n - 1
+                yield ("wait", tmem_empty[last & 1], (last >> 1) & 1)
+                if n > 1:
+                    prev = n - 2
+                    yield ("wait", tmem_empty[prev & 1], (prev >> 1) & 1)
+
+        def scheduler(clc_full=clc_full, clc_empty=clc_empty, resp=resp, pre=pre):
+            who = pre + "scheduler"
+            it = TileIter()
+            stage = phase = 0
+            it.more = it.tile < tiles
+            while it.more:
+                if bug != "no_clc_empty":
+                    yield ("wait", clc_empty[stage], phase ^ 1)
+                yield ("expect_tx", clc_full[0][stage], 16)
+                yield ("expect_tx", clc_full[1][stage], 16)
+                yield ("clc", [resp[0][stage], resp[1][stage]], [clc_full[0][stage], clc_full[1][stage]], who)
+                stage = 0 if stage + 1 == clc_stages else stage + 1
+                phase ^= 1 if stage == 0 else 0
+                yield from tile_next(it, 0, who)
+
+        def epilogue(c, w, acc=acc, tmem_full=tmem_full, tmem_empty=tmem_empty, pre=pre):
+            who = pre + f"epi{c}_{w}"
+            it = TileIter()
+            n = 0
+            it.more = it.tile < tiles
+            while it.more:
+                a, aphase = n & 1, (n >> 1) & 1
+                yield ("wait", tmem_full[c][a], aphase)
+                for _ in range(s.rng.randrange(epi_delay + 1)):
+                    yield ("nop",)
+                yield ("gemm_acc_read", acc[a], it.tile, who)
+                yield ("arrive", tmem_empty[a])
+                done_tiles[(it.tile, c, w)] = done_tiles.get((it.tile, c, w), 0) + 1
+                n += 1
+                yield from tile_next(it, c, who)
+
+        s.threads[pre + "producer0"] = producer(0)
+        s.threads[pre + "producer1"] = producer(1)
+        s.threads[pre + "mma"] = mma()
+        if use_clc:
+            s.threads[pre + "scheduler"] = scheduler()
+        for c in range(2):
+            for w in range(epi_warps):
+                s.threads[pre + f"epi{c}_{w}"] = epilogue(c, w)
+
+    for cl_ in range(clusters):
+        build(cl_)
+
+    base_do = s.do
+
+    def do(who, act):
+        kind = act[0]
+        if kind == "nop":
+            pass
+        elif kind == "expect_tx":
+            act[1].expect_tx(act[2])
+        elif kind == "gemm_tma":  # one CTA's half of a k-block into its own stage; bytes counted on the leader's barrier
+            _, b, bar, nbytes, tag, _who = act
+            b.check_writable(who)
+            b.write_pending = True
+
+            def landed():
+                b.write_pending = False
+                b.version += 1
+                b.tag = tag
+                bar.complete_tx(nbytes)
+            s.tma_events.append(landed)
+        elif kind == "gemm_mma":  # reads both CTAs' stage, accumulates into (or overwrites) the TMEM buffer
+            _, bufs, tag, accb, first, _who = act
+            for b in bufs:
+                if b.write_pending:
+                    raise ProtocolError(f"{who}: {b.name} read while a TMA write is in flight")
+                if b.tag != tag:
+                    raise ProtocolError(f"{who}: {b.name} holds k-block {b.tag}, expected {tag}")
+                b.async_reads += 1
+            if first:
+                if accb.async_reads:
+                    raise ProtocolError(f"{who}: {accb.name} overwritten while MMAs still read it")
+                if accb.version > 0 and accb.sync_reads.get(accb.version, 0) < accb.warps:
+                    raise ProtocolError(f"{who}: {accb.name} (tile {accb.tag}) overwritten before all {accb.warps} "
+                                        f"epilogue warps read it ({accb.sync_reads.get(accb.version, 0)} did)")
+                accb.version += 1
+                accb.tag = tag[0]
+            elif accb.tag != tag[0]:
+                raise ProtocolError(f"{who}: accumulating tile {tag[0]} into {accb.name} which holds tile {accb.tag}")
+            accb.write_pending = True
+
+            def done():
+                for b in bufs:
+                    b.async_reads -= 1
+                accb.write_pending = False
+            s.mma_queue.append(done)
+        elif kind == "commit2":  # multicast tcgen05.commit: arrives on both CTAs' barriers once prior MMAs completed
+            bars = act[1]
+            s.mma_queue.append(lambda: [b.arrive() for b in bars])
+        elif kind == "gemm_acc_read":
+            _, accb, tile, _who = act
+            if accb.write_pending:
+                raise ProtocolError(f"{who}: {accb.name} read while MMAs are still writing it")
+            if accb.tag != tile:
+                raise ProtocolError(f"{who}: reads {accb.name} for tile {tile} but it holds tile {accb.tag}")
+            accb.sync_reads[accb.version] = accb.sync_reads.get(accb.version, 0) + 1
+        elif kind == "clc":  # clusterlaunchcontrol.try_cancel, response multicast to both CTAs
+            _, resps, bars, _who = act
+            for r in resps:
+                if r.write_pending:
+                    raise ProtocolError(f"{who}: CLC request into {r.name} while the previous one is in flight")
+                r.write_pending = True
+
+            def answered():
+                t = state["next"] if state["next"] < tiles else None
+                if t is not None:
+                    state["next"] += 1
+                for r, b in zip(resps, bars):
+                    r.write_pending = False
+                    r.version += 1
+                    r.tag = t
+                    b.complete_tx(16)
+            s.tma_events.append(answered)
+        else:
+            base_do(who, act)
+
+    s.do = do
+    s.run()
+    # every tile exactly once, by every epilogue warp of both CTAs of exactly one pair
+    for t in range(tiles):
+        for c in range(2):
+            for w in range(epi_warps):
+                if done_tiles.get((t, c, w), 0) != 1:
+                    raise ProtocolError(f"tile {t} processed {done_tiles.get((t, c, w), 0)} times by epilogue warp {c}/{w}")
+    return s
+
 if __name__ == "__main__":
     for seed in range(200):
         model_bwd(seed, 1, 4, 2, 4, True, False)
@@ -504,4 +773,5 @@ if __name__ == "__main__":
         model_bwd(seed, 3, 3, 2, 8, False, True)
         model_fwd_persist(seed, 3, 4)  # softmax + separate epilogue warps (round-2 kernel)
         model_fwd_long(seed, 9)
+        model_gemm(seed, 9, clusters=2, epi_warps=2)
     print("all protocols passed 200 schedules each")
