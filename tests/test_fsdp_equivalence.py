@@ -31,6 +31,8 @@ def baseline(tmp_path_factory):
     (2, {"shard_on_cpu": True, "flatten": True, "grad_ckpt": False, "reshard": False}),
     (2, {"no_fsdp": True}),
     (4, {}),
+    (8, {}),                                   # the flagship world size: one image per rank, 8-way shards with padding
+    (8, {"flatten": True, "reshard": False}),
     (1, {"flatten": True, "grad_ckpt": False}),
     (1, {"no_fsdp": True}),
 ])
