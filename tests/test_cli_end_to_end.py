@@ -126,14 +126,17 @@ def test_every_strategy_flag_through_the_cli_gives_the_same_trajectory(tmp_path)
         "keep_all": ["--nproc", "2", "--ckpt_keep_blocks", "2"],
         "single": ["--nproc", "1"],
     }
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    procs = {name: subprocess.Popen([sys.executable, "run_vit_training.py", *base, *extra, "--ckpt_dir",
+                                     str(tmp_path / name), "--num_epochs", "1"], cwd=ROOT, env=env,
+                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for name, extra in variants.items()}  # the six jobs are independent: run them side by side
     losses = {}
-    for name, extra in variants.items():
-        r = _run(["run_vit_training.py", *base, *extra, "--ckpt_dir", str(tmp_path / name), "--num_epochs", "1"])
-        assert r.returncode == 0, name + r.stdout[-2000:] + r.stderr[-2000:]
-        losses[name] = [float(x) for x in re.findall(r"loss: ([0-9.]+)", r.stdout)]
-        assert len(losses[name]) == 3, (name, r.stdout[-1500:])
-        if name == "ddp":
-            assert "per-GPU (sharded) parameter num" in r.stdout or "parameter num" in r.stdout
+    for name, proc in procs.items():
+        out, err = proc.communicate(timeout=600)
+        assert proc.returncode == 0, name + out[-2000:] + err[-2000:]
+        losses[name] = [float(x) for x in re.findall(r"loss: ([0-9.]+)", out)]
+        assert len(losses[name]) == 3, (name, out[-1500:])
     ref = losses["zero3"]
     assert ref[2] < ref[0]
     for name, ls in losses.items():
