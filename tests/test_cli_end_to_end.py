@@ -142,3 +142,22 @@ def test_every_strategy_flag_through_the_cli_gives_the_same_trajectory(tmp_path)
     for name, ls in losses.items():
         for a, b in zip(ls, ref):
             assert abs(a - b) < 2e-3, (name, ls, ref)
+
+
+def test_a_dying_rank_takes_the_job_down_and_resume_continues(tmp_path):
+    """Failure contract: a rank that crashes mid-epoch must not leave its peers hanging in a collective --
+    the launcher exits non-zero in bounded time -- and the run continues from the last checkpoint with --resume_epoch."""
+    ckpt = str(tmp_path / "ckpt")
+    ok = _run(["run_vit_training.py", *TINY, "--ckpt_dir", ckpt, "--num_epochs", "1"])
+    assert ok.returncode == 0, ok.stdout[-2000:] + ok.stderr[-2000:]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", B200_INJECT_FAILURE="1:2:2")
+    bad = subprocess.run([sys.executable, "run_vit_training.py", *TINY, "--ckpt_dir", ckpt, "--num_epochs", "3",
+                          "--resume_epoch", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0
+    assert "[fault injection] rank 1 dies at epoch 2 step 2" in bad.stdout
+    assert "training completed" not in bad.stdout
+    assert not os.path.exists(os.path.join(ckpt, "epoch_2_rank_0.ckpt"))  # nothing half-written was left behind
+    again = _run(["run_vit_training.py", *TINY, "--ckpt_dir", ckpt, "--num_epochs", "3", "--resume_epoch", "1"])
+    assert again.returncode == 0, again.stdout[-2000:] + again.stderr[-2000:]
+    assert "starting epoch 2" in again.stdout and "training completed" in again.stdout
+    assert os.path.exists(os.path.join(ckpt, "epoch_3_rank_1.ckpt"))

@@ -161,6 +161,17 @@ def evaluate(rt: Runtime, loader, model: FSDPViT, max_steps: int = 0):
 eval_on_val = evaluate  # reference name (run_vit_training.py:303)
 
 
+def fault_injection_point(rank: int, epoch: int, step: int) -> None:
+    """``B200_INJECT_FAILURE=<rank>:<epoch>:<step>`` makes that rank die there without any clean-up (as a crashed
+    process would).  Used by the tests of the failure contract: the launcher tears the job down with a non-zero exit
+    code instead of leaving the survivors hanging in a collective, and ``--resume_epoch`` continues from the last
+    checkpoint (the reference's contract: README.md:100, run_vit_training.py:246-248)."""
+    spec = os.environ.get("B200_INJECT_FAILURE")
+    if spec and spec == f"{rank}:{epoch}:{step}":
+        print(f"[fault injection] rank {rank} dies at epoch {epoch} step {step}", flush=True)
+        os._exit(13)
+
+
 class Trainer:
     def __init__(self, rt: Runtime, cfg):
         self.rt, self.cfg = rt, cfg
@@ -220,6 +231,7 @@ class Trainer:
         host_t = time.time()
         since_log = 0
         for step, (images, target) in enumerate(self.train_loader):
+            fault_injection_point(rt.rank, epoch, step + 1)
             loss = self.step_fn(images, target)
             self.lr_scheduler.step()
             self.optimizer.zero_grad(set_to_none=True)
