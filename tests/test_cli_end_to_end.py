@@ -20,10 +20,15 @@ def _run(args, timeout=300):
 
 def test_train_resume_consolidate_via_cli(tmp_path):
     ckpt = str(tmp_path / "ckpt")
-    r = _run(["run_vit_training.py", *TINY, "--ckpt_dir", ckpt, "--num_epochs", "1"])
+    jsonl = str(tmp_path / "steps.jsonl")
+    r = _run(["run_vit_training.py", *TINY, "--ckpt_dir", ckpt, "--num_epochs", "1", "--bench_json", jsonl])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = r.stdout
     assert "training completed" in out and "accuracy on val" in out
+    import json
+    rows = [json.loads(line) for line in open(jsonl)]  # --bench_json: one JSON line per logged step, rank 0 only
+    assert [row["step"] for row in rows] == [1, 2, 3] and all(row["images_per_sec"] > 0 for row in rows)
+    assert rows[0]["lr"] == 0.005 and rows[-1]["loss"] < rows[0]["loss"]
     assert "epoch 1 step 1, lr:" in out and "sec/iter" in out  # the reference's log line
     for rank in (0, 1):
         assert os.path.exists(os.path.join(ckpt, f"epoch_1_rank_{rank}.ckpt"))

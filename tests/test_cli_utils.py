@@ -148,3 +148,22 @@ def test_pod_launcher_builds_per_host_commands(capsys):
         assert "NCCL_DEBUG=WARN" in ln and "FOO='a b'" in ln and "cd /srv/vit" in ln
         assert ln.endswith("run_vit_training.py --fake_data --batch_size 1024")
     assert "pkill" not in a and "killall" not in a  # restarts stop the recorded PID, never a pattern
+
+
+def test_runtime_host_helpers_single_process():
+    """xm.* replacements (launch.Runtime): master_print, mesh_reduce, step closures, memory info."""
+    from vit_10b_fsdp_example_b200.launch import Runtime
+
+    rt = Runtime(rank=0, world=1, local_rank=0, device=torch.device("cpu"))
+    assert rt.mesh_reduce("tag", 3, sum) == 3 and rt.mesh_reduce("tag", 2.5, max) == 2.5
+    seen = []
+    rt.add_step_closure(lambda a, b: seen.append((a, b)), args=(1, 2))
+    rt.add_step_closure(lambda a: seen.append(a), args=("x",))
+    assert seen == []           # closures run after the step, not when they are added
+    rt.run_step_closures()
+    assert seen == [(1, 2), "x"]
+    rt.run_step_closures()
+    assert seen == [(1, 2), "x"]  # each closure runs once
+    info = rt.get_memory_info()
+    assert info["kb_total"] >= info["kb_free"] >= 0
+    rt.rendezvous("no-op on one process")
