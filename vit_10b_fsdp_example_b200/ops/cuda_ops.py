@@ -4,8 +4,10 @@ Every function launches hand-written kernels from ``_C.so``:
   * GEMMs: persistent 2-CTA tcgen05 kernel with TMEM accumulators and fused epilogues
     (bias / GELU / dGELU / residual / pre-activation side output / bias-gradient column sums);
     forward (NT), dgrad (NN) and wgrad (TN) run on the same kernel via K-major / MN-major descriptors.
-  * attention core: batched tcgen05 GEMMs that read q/k/v in place from the packed qkv buffer through
-    4-D TMA tensor maps + a fused scale/softmax kernel (fwd) and softmax-backward kernel (bwd).
+  * attention core: fused tcgen05 forward (keeps the row log-sum-exp) + fused backward kernels that read q/k/v in
+    place from the packed qkv buffer through 4-D TMA tensor maps; scores never reach HBM.  The un-fused path (batched
+    tcgen05 GEMMs + softmax / softmax-backward kernels with materialised P) remains for attention dropout and
+    B200_FUSED_ATTN_BWD=0.
   * LayerNorm fwd/bwd, cross-entropy, im2col, column sums, sum of squares, fused AdamW.
 
 What each group replaces in the reference (all of it reached through timm / torch_xla there):
@@ -214,8 +216,8 @@ FUSED_ATTENTION_HD160 = _os.environ.get("B200_FUSED_ATTN_HD160", "0") == "1"
 
 
 # Persistent, software-pipelined kernels (csrc/attention_persist_sm100.cu, attention_bwd_persist_sm100.cu): one CTA per
-# SM loops over work items.  They win where only one CTA fits an SM (hd = 160: forward 632 vs 763 us one-shot, backward
-# 1622 vs 1814 us) and lose where two fit (hd = 64: 254 vs 159 us), hence the per-shape default below.
+# SM loops over work items.  They win where only one CTA fits an SM (hd = 160, round-2 kernels: forward 311 vs 763 us
+# one-shot, backward 1352 vs 1814 us) and lose where two fit (hd = 64: 254 vs 159 us), hence the per-shape default below.
 _PERSIST_ENV = _os.environ.get("B200_ATTN_PERSIST", "")
 ATTN_PERSIST = _PERSIST_ENV == "1"
 
@@ -264,9 +266,9 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop=None, need_p: bool 
         out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
         _C.attention_fwd_persist(qkv, out, None, B, N, H, hd)
         return out, None
-    # hd <= 128: two CTAs fit an SM and the fused kernel is ~1.8x faster than GEMM+softmax+GEMM (ViT-L: 159 vs 279 us).
-    # hd = 160 (ViT-10B) needs 200 KB of smem -> one CTA per SM with nothing to overlap its loads; measured slower
-    # than the batched-GEMM path (764 vs 664 us), so that shape stays on the un-fused path unless forced.
+    # hd <= 128: two CTAs fit an SM and the one-shot fused kernel is ~1.8x faster than GEMM+softmax+GEMM (ViT-L: 159 vs
+    # 279 us).  hd = 160 (ViT-10B) needs 200 KB of smem -> one CTA per SM: that shape runs the persistent kernel above
+    # (311 us); the one-shot kernel (764 us) loses to the batched-GEMM path (664 us) there and is only used when forced.
     if FUSED_ATTENTION and _C.attention_fwd_supported(N, hd) and (hd <= 128 or FUSED_ATTENTION_HD160):
         # one fused tcgen05 kernel per (image, head, 128-query block): S and P live in TMEM / shared memory
         out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
@@ -299,8 +301,8 @@ def attention_fwd(qkv, B: int, N: int, H: int, hd: int, drop=None, need_p: bool 
 #   ViT-L  (B128 N196 H16 hd64) : fused 159 + 387 us   vs un-fused 279 + 500 + 204 us   -> fused by default
 #   336 px (B56 N576 H32 hd160) : fused 1584 + 3032 us vs un-fused 1424 + 2459 + 1088 us, and P alone would be
 #                                 1.2 GB per block                                       -> fused by default
-#   ViT-10B (B128 N256 H32 hd160): fused (persistent) 632 + 1622 us vs un-fused 664 + 1356 (+426 if P is not kept)
-#                                 -> un-fused while HBM can hold P, see use_flash()
+#   ViT-10B (B128 N256 H32 hd160): fused (persistent, round 2) 311 + 1352 us vs un-fused 664 + 1356 (+426 if P is not
+#                                 kept), and no 512 MiB of P per block                   -> fused by default
 # B200_FUSED_ATTN_BWD=0 / 1 forces the choice.
 _FLASH_ENV = _os.environ.get("B200_FUSED_ATTN_BWD", "")
 FLASH_ATTENTION = _FLASH_ENV != "0"
