@@ -110,3 +110,30 @@ def test_keep_policy_is_sized_after_the_first_step_of_this_process_even_when_res
     assert calls == [] and model.keep_blocks == -1 and model.step_count == 8
     model.forward_backward(x, y)
     assert calls == [2] and model.keep_blocks == 1
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("which", ["vit10b_root", "vitl_block", "vitl_root"])
+def test_tables_on_the_real_units_with_awkward_shapes(world, which):
+    """Real unit shapes: the ViT-10B root unit (patch embedding zero-padded to the TMA-legal K, position embedding,
+    1000-class head: 125 rows and a 125-element bias slice per rank at W = 8) and ViT-L.  Every segment must stay a whole
+    number of 16-byte vectors and cover its buffer exactly once, for the gather and for the reduce-scatter."""
+    cfg = ViTConfig() if which == "vit10b_root" else ViTConfig(embed_dim=1024, num_heads=16, num_blocks=24, patch_size=16)
+    specs = vit.root_param_specs(cfg) if which.endswith("root") else vit.block_param_specs(cfg)
+    lay = UnitLayout.build("u", specs, world, False)
+    es = 2
+    assert lay.shard_numel * world == lay.full_numel
+    for rank in (0, world - 1):
+        be = _fake(world, rank)
+        table, chunks = backends.Sm100Backend._ag_table(be, lay, es)
+        cover = torch.zeros(lay.full_numel * es, dtype=torch.int8)
+        for r, src_off, dst_off, n, pf in table.tolist():
+            assert n % 16 == 0 and src_off % 16 == 0 and dst_off % 16 == 0
+            cover[dst_off: dst_off + n] += 1
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        rs, rchunks = backends.Sm100Backend._rs_table(be, lay, es)
+        scover = torch.zeros(lay.shard_numel, dtype=torch.int8)
+        for foff_b, soff, n, pf in rs.tolist():
+            assert foff_b % 16 == 0 and (soff * 4) % 16 == 0 and (n * es) % 16 == 0
+            scover[soff: soff + n] += 1
+        assert int(scover.min()) == 1 and int(scover.max()) == 1
