@@ -39,7 +39,7 @@ def _sha(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())  # not the absolute path: the snapshot on a GPU box lives elsewhere
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
