@@ -80,3 +80,36 @@ def test_consolidated_checkpoint_round_trip(tmp_path):
         want = plain(images)
     got = ref.eval()(images)
     assert torch.allclose(got, want, atol=1e-4), (got - want).abs().max()
+
+
+def test_consolidated_checkpoints_of_other_stacks_load_after_key_normalisation(tmp_path):
+    """Migration path for users of the reference: a consolidated state_dict whose names still carry wrapper prefixes
+    (torch_xla FSDP's `_fsdp_wrapped_module.` / `_fpw_module.`, DDP's `module.`) and timm's 4-D patch-embedding
+    weight loads into the engine."""
+    from vit_10b_fsdp_example_b200.utils.checkpoint import normalize_full_state_dict_keys
+
+    cfg = tiny_cfg()
+    src = FSDPViT(cfg, dtype=torch.float32, seed=3)
+    full = full_params_of(src)
+    foreign = {}
+    for k, v in full.items():
+        if k.startswith("blocks."):
+            i, rest = k.split(".", 2)[1:]
+            k2 = f"module._fsdp_wrapped_module._fpw_module.blocks.{i}._fsdp_wrapped_module._fpw_module.{rest}"
+        else:
+            k2 = "module._fsdp_wrapped_module._fpw_module." + k
+        if k == "patch_embed.proj.weight":  # timm stores the conv kernel as [D, 3, P, P]
+            v = v[:, : 3 * cfg.patch_size ** 2].reshape(cfg.embed_dim, 3, cfg.patch_size, cfg.patch_size)
+        foreign[k2] = v.clone()
+    clean = normalize_full_state_dict_keys(foreign)
+    assert set(clean) == set(full)
+    dst = FSDPViT(cfg, dtype=torch.float32, seed=11)
+    dst.load_full_state_dict(clean)
+    got = full_params_of(dst)
+    for k in full:
+        assert torch.equal(got[k], full[k]), k
+    # already-clean names pass through; colliding names are an error, not a silent overwrite
+    assert set(normalize_full_state_dict_keys(full)) == set(full)
+    import pytest
+    with pytest.raises(KeyError):
+        normalize_full_state_dict_keys({"module.head.bias": 1, "head.bias": 2})

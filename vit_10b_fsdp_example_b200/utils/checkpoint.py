@@ -43,3 +43,24 @@ def load_ckpt(ckpt_path: str, model, optimizer, lr_scheduler) -> None:
         model.step_count = int(optimizer.state[model.all_units[0].name]["step"])
     lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
     print(f"resumed from checkpoint {ckpt_path}\n", end="")
+
+
+_WRAPPER_PARTS = ("_fsdp_wrapped_module.", "_fpw_module.", "_checkpoint_wrapped_module.", "_orig_mod.")
+
+
+def normalize_full_state_dict_keys(state: dict) -> dict:
+    """Strip wrapper prefixes from the parameter names of a consolidated checkpoint so that one written by another
+    stack loads here: torch_xla FSDP (``_fsdp_wrapped_module.`` / ``_fpw_module.``, what the reference's
+    ``consolidate_sharded_ckpts`` may leave behind), PyTorch FSDP / activation-checkpoint wrappers, DDP's leading
+    ``module.`` and torch.compile's ``_orig_mod.``.  Names that are already timm-style pass through unchanged."""
+    out = {}
+    for k, v in state.items():
+        name = k
+        for part in _WRAPPER_PARTS:
+            name = name.replace(part, "")
+        while name.startswith("module."):
+            name = name[len("module."):]
+        if name in out:
+            raise KeyError(f"checkpoint keys {k!r} and another entry both normalise to {name!r}")
+        out[name] = v
+    return out
